@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the FastSVC generator forward (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port), rank 0 only
+
+A "step" = one generator forward over one batch of synthetic input (BASELINE
+config 2: batch 32, 1-second clips = 16000 samples, YAML generator config).
+For N > 1 launch under torchrun (one rank per GPU): every rank runs its own
+batch of 32 (weak scaling, no data-path collective: inference shards by
+utterance); the step time is the max over ranks.
+
+Prints ONE JSON line on rank 0 (contract: see the task statement / DESIGN.md).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "audio samples/sec (generator fwd, bs32, 16k-sample clips)"
+UNIT = "samples/s"
+B, FRAMES = 32, 100          # BASELINE configs[1]: batch 32, 1-second clips
+L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+
+
+def _peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=smax, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+def _inputs(rank):
+    from svcc23_fastsvc_b200 import synthetic as syn
+    params = syn.make_params(syn.YAML_CONFIG, seed=0)
+    ppg, sine, lft, spk = syn.make_inputs(B, FRAMES, syn.YAML_CONFIG, seed=1234 + rank)
+    return params, ppg, sine, lft, spk
+
+
+def _cpu_reference_forward(params, ppg, sine, lft, spk, nb):
+    """One forward of the reference's op sequence (oracle/fastsvc_torch.py, recompute=True) on the host CPU."""
+    import torch
+    from oracle import fastsvc_torch as otorch
+    tp = {k: torch.from_numpy(v) for k, v in params.items()}
+    args = [torch.from_numpy(a[:nb]) for a in (ppg, sine, lft, spk)]
+    with torch.no_grad():
+        return otorch.generator_forward(tp, *args, recompute=True)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the Python reference
+    itself cannot travel to the GPU box), all host threads, bounded sample per step."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nb = 4  # utterances per reference step (bounded sample of the 32-utterance batch)
+    params, ppg, sine, lft, spk = _inputs(0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        _cpu_reference_forward(params, ppg, sine, lft, spk, nb)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _cpu_reference_forward(params, ppg, sine, lft, spk, nb)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = nb * FRAMES * 160 / dt
+    sample = f"{nb} of the 32 utterances per step (16000-sample clips), fp32, torch CPU ops in the reference's order"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch 32 x 16000-sample clips, YAML generator (bounded sample: "
+                               f"{nb} utterances/step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import harana.models as M
+    from svcc23_fastsvc_b200 import synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T = FRAMES * 160
+
+    params, ppg, sine, lft, spk = _inputs(rank)
+    g = M.FastSVCGenerator(**{k: (list(v) if isinstance(v, list) else v) for k, v in syn.YAML_CONFIG.items()})
+    g.remove_weight_norm()
+    g.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    g = g.eval().to(dev)
+    g.precision = args.precision
+    host = [torch.from_numpy(a).pin_memory() for a in (ppg, sine, lft, spk)]
+    devin = [t.to(dev) for t in host]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    out_host = torch.empty((B, 1, T), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                         # evict L2 between timed iterations (outside the event pair)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ms = timed(lambda: g(*devin), args.steps, args.warmup)
+        launches = g.last_launch_count()
+        ms_e2e = timed(lambda: g.forward_host(*host, out=out_host), args.steps, max(3, args.warmup // 2))
+        clocks = sampler.stop() if rank == 0 else None
+
+        # parity of what was just timed (rank 0, 2 utterances vs the CPU oracle port)
+        parity = None
+        roof, cpu_base, eager = None, None, None
+        if rank == 0:
+            y = g(*devin)[:2].cpu()
+            ref = _cpu_reference_forward(params, ppg, sine, lft, spk, 2)
+            parity = float((y - ref).abs().max())
+            # per-kernel profile (CUDA events around every launch, on the launching stream)
+            recs = None
+            for _ in range(3):
+                flush.zero_()
+                recs = g.profile(*devin)
+            total = sum(r["ms"] for r in recs)
+            agg = {}
+            for r in recs:
+                kind = r["label"]
+                a = agg.setdefault(kind, dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+                a["ms"] += r["ms"]; a["flops"] += r["flops"]; a["bytes"] += r["bytes"]; a["n"] += 1
+            top = max(agg.items(), key=lambda kv: kv[1]["ms"])
+            peaks = _peaks()
+            name, a = top
+            achieved = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": name,
+                    "kernel_ms": a["ms"], "kernel_share_of_step": a["ms"] / total,
+                    "kernel_tflops": a["flops"] / (a["ms"] * 1e-3) / 1e12, "peak_source": peaks["source"],
+                    "byte_model": "layer-boundary (M3): every operand tensor of the launch touched once, fp32",
+                    "whole_forward": {"ms_sum_of_kernels": total,
+                                      "algorithmic_gflop": sum(r["flops"] for r in recs) / 1e9,
+                                      "tflops": sum(r["flops"] for r in recs) / (total * 1e-3) / 1e12,
+                                      "M2_stage_boundary_GB": 0.66,
+                                      "M2_frac_of_hbm_peak": 0.66 / (total * 1e-3) / peaks["hbm_gbs"]},
+                    "top5": [dict(kernel=k, ms=v["ms"], share=v["ms"] / total,
+                                  gbs=v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+                                  tflops=v["flops"] / (v["ms"] * 1e-3) / 1e12)
+                             for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:5]]}
+            # CPU baseline: the reference's op sequence on the host cores, bounded sample
+            nb, reps = 8, 3
+            _cpu_reference_forward(params, ppg, sine, lft, spk, nb)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                _cpu_reference_forward(params, ppg, sine, lft, spk, nb)
+            dt = (time.perf_counter() - t0) / reps
+            cpu_base = {"value": nb * T / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{reps} forwards of {nb} utterances x 16000 samples (of the 32-utterance batch), "
+                                  f"fp32 torch CPU ops in the reference's order, host has {os.cpu_count()} cpus"}
+            # the reference's op sequence through stock PyTorch eager on this GPU (denominator of the 20x target)
+            if not args.no_eager:
+                from oracle import fastsvc_torch as otorch
+                torch.backends.cudnn.benchmark = True     # train_fastsvc.py:617
+                tp = {k: torch.from_numpy(v).to(dev) for k, v in params.items()}
+                ems = timed(lambda: otorch.generator_forward(tp, *devin, recompute=True), 10, 5) if world == 1 else None
+                if ems:
+                    eager = {"ms_per_step": ems, "value": B * T / (ems * 1e-3), "unit": UNIT,
+                             "what": "reference op sequence, PyTorch eager CUDA fp32 (cuDNN), same inputs"}
+
+    if rank == 0:
+        h2d = sum(t.numel() * 4 for t in host)
+        d2h = out_host.numel() * 4
+        line = {
+            "metric": METRIC, "value": world * B * T / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch 32/GPU x 16000-sample clips (100 PPG frames), YAML generator "
+                                   "in=144 mid=[192,96,48,24] scales=[2,4,4,5] spk=512",
+                       "precision_mode": g.precision, "l2": "flushed (256 MiB memset) between timed iterations",
+                       "parallelism": f"utterance-sharded x{world}, no collectives"},
+            "e2e": {"value": world * B * T / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "gpu_launches": launches * args.steps,
+            "launches_per_step": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu_base,
+            "torch_eager_cuda": eager,
+            "parity_max_abs_vs_oracle": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("FSVC_MODE", "auto"))
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-CUDA comparison leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
