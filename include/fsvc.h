@@ -121,12 +121,12 @@ int fsvc_forward_host(fsvc_handle* h, const float* ppg_host, const float* sine_h
  * (fastsvc.py:180-193): w[] = {residual_block.0 (w,b), downsample_block.2
  * (w,b), .4 (w,b), .6 (w,b)}; x (B,Cin,T) -> out (B,C,T/scale); T % scale == 0. */
 int fsvc_downsample_forward(const float* x, float* out, const float* const* w, int B, int c_in, int c, int T,
-                            int scale, float slope, void* workspace, size_t workspace_bytes, void* stream);
+                            int scale, float slope, void* workspace, size_t workspace_bytes, int mode, void* stream);
 /* fsvc_film_forward replaces FastSVCFiLMNet.forward (fastsvc.py:220-232):
  * w[] = {conv (w,b), conv_scale (w,b), conv_shift (w,b)}; x (B,C,T) ->
  * scale (B,C,T), shift (B,C,T). */
 int fsvc_film_forward(const float* x, float* scale, float* shift, const float* const* w, int B, int c, int T,
-                      float slope, void* workspace, size_t workspace_bytes, void* stream);
+                      float slope, void* workspace, size_t workspace_bytes, int mode, void* stream);
 /* fsvc_upsample_forward replaces FastSVCUpsampleNet.forward
  * (fastsvc.py:80-140): w[] = {conv_first, upsample_block0.2, conv_block1.1,
  * conv_block2.1, conv_block3.1, residual_block.1, emb_projector} (w,b each; the
@@ -135,7 +135,7 @@ int fsvc_film_forward(const float* x, float* scale, float* shift, const float* c
 int fsvc_upsample_forward(const float* x, const float* s_scale, const float* s_shift, const float* l_scale,
                           const float* l_shift, const float* spk, float* out, const float* const* w, int B,
                           int c_in, int c, int T, int scale, int spk_emb_size, float slope, float eps,
-                          void* workspace, size_t workspace_bytes, void* stream);
+                          void* workspace, size_t workspace_bytes, int mode, void* stream);
 size_t fsvc_block_workspace_bytes(int B, int c_in, int c, int T_out);
 
 /* Profiling variant of fsvc_forward (NOT graph-capturable: it creates CUDA

@@ -86,12 +86,12 @@ def load():
     lib.fsvc_forward_host.restype = i32
     lib.fsvc_forward_host.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, i32, vp]
     lib.fsvc_downsample_forward.restype = i32
-    lib.fsvc_downsample_forward.argtypes = [vp, vp, pp, i32, i32, i32, i32, i32, fp, vp, sz, vp]
+    lib.fsvc_downsample_forward.argtypes = [vp, vp, pp, i32, i32, i32, i32, i32, fp, vp, sz, i32, vp]
     lib.fsvc_film_forward.restype = i32
-    lib.fsvc_film_forward.argtypes = [vp, vp, vp, pp, i32, i32, i32, fp, vp, sz, vp]
+    lib.fsvc_film_forward.argtypes = [vp, vp, vp, pp, i32, i32, i32, fp, vp, sz, i32, vp]
     lib.fsvc_upsample_forward.restype = i32
     lib.fsvc_upsample_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, pp, i32, i32, i32, i32, i32, i32, fp, fp,
-                                          vp, sz, vp]
+                                          vp, sz, i32, vp]
     lib.fsvc_block_workspace_bytes.restype = sz
     lib.fsvc_block_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.fsvc_forward_profile.restype = i32

@@ -52,6 +52,7 @@ struct ConvArgs {
   float2* stats;  // [B][C_out][n_tiles] (mean, M2) or nullptr
   int n_tiles;
   float slope;
+  const void* host_w;  // host-side ConvW* (launch dispatch only; never dereferenced on the device)
 };
 
 constexpr int kConvThreads = 256;

@@ -10,6 +10,7 @@
 
 #include "../../include/fsvc.h"
 #include "conv_f32.cuh"
+#include "conv_tc.cuh"
 
 namespace fsvc {
 
@@ -33,7 +34,24 @@ struct ConvW {  // packed [C_in][K][C_out] + bias[C_out], device
   float* w = nullptr;
   float* b = nullptr;
   int C_in = 0, C_out = 0, K = 0;
+  TcW tc;  // tensor-core copy of the same weights (tc.w == nullptr: conv not eligible)
 };
+
+// Tensor-core tiling of a conv: N tiles of <= 128 output channels (multiple of 16), input-channel
+// blocks of <= 64 (multiple of 16).  Tiny convs (C_in or C_out < 8) stay on the fp32 kernel.
+static bool tc_plan(int C_in, int C_out, int K, TcW* t) {
+  if (C_in < 8 || C_out < 8) return false;
+  const int n16 = (C_out + 15) / 16 * 16;
+  t->n_ntiles = (n16 + 127) / 128;
+  t->N_tile = ((n16 + t->n_ntiles - 1) / t->n_ntiles + 15) / 16 * 16;
+  t->N_alloc = 32;
+  while (t->N_alloc < t->N_tile) t->N_alloc *= 2;
+  const int c16 = (C_in + 15) / 16 * 16;
+  t->n_blk = (c16 + 63) / 64;
+  t->CIB = ((c16 + t->n_blk - 1) / t->n_blk + 15) / 16 * 16;
+  t->K = K;
+  return true;
+}
 
 struct WeightInfo {
   std::string name;
@@ -63,6 +81,9 @@ struct fsvc_handle {
   std::vector<WeightInfo> winfo;
   float* store = nullptr;
   size_t store_floats = 0;
+  __nv_bfloat16* tc_store = nullptr;  // tensor-core (bf16 hi/lo) copies of the conv weights
+  size_t tc_elems = 0;
+  std::vector<ConvW*> convs;          // every conv of the generator (for the tensor-core repack)
   StageW stage[FSVC_MAX_STAGES];
   LevelW level[FSVC_MAX_STAGES];
   ConvW last;
@@ -109,6 +130,7 @@ struct Ctx {
   int err = 0;
   Profiler* prof = nullptr;
   const char* label = "";
+  bool tc = false;  // use the tcgen05 kernels where a conv is eligible
   // profiling bookkeeping: called right after a kernel launch
   void launched(const char* kind, double flops, double bytes) {
     launches++;
@@ -148,7 +170,27 @@ static int conv_rc(int C_out) {
   return 6;
 }
 
+static bool use_tc(const Ctx& c, const ConvW& w) { return c.tc && w.tc.w != nullptr; }
+
+static void launch_conv_tc(Ctx& c, const ConvArgs& a, const TcW& t) {
+  TcArgs p;
+  p.c = a;
+  p.w = t.w;
+  p.CIB = t.CIB;
+  p.n_blk = t.n_blk;
+  p.N_tile = t.N_tile;
+  p.N_alloc = t.N_alloc;
+  const size_t smem = tc_smem_bytes(t.K, a.dil, t.CIB, t.n_blk, t.N_tile);
+  dim3 grid((a.T_out + kTcM - 1) / kTcM, t.n_ntiles, c.B);
+  if (t.K == 3) conv1d_tc_kernel<3><<<grid, kTcThreads, smem, c.stream>>>(p);
+  else conv1d_tc_kernel<1><<<grid, kTcThreads, smem, c.stream>>>(p);
+}
+
 static void launch_conv(Ctx& c, const ConvArgs& a, int K, const char* name = "conv") {
+  const ConvW* cw = (const ConvW*)a.host_w;
+  if (cw && use_tc(c, *cw)) {
+    launch_conv_tc(c, a, cw->tc);
+  } else {
   const int rc = conv_rc(a.C_out), rt = conv_rt(a.T_out);
 #define FSVC_CASE(RC_, RT_)                                                  \
   if (rc == RC_ && rt == RT_) {                                              \
@@ -158,6 +200,7 @@ static void launch_conv(Ctx& c, const ConvArgs& a, int K, const char* name = "co
   FSVC_CASE(1, 4) FSVC_CASE(1, 8) FSVC_CASE(2, 4) FSVC_CASE(2, 8) FSVC_CASE(3, 4) FSVC_CASE(3, 8)
   FSVC_CASE(4, 4) FSVC_CASE(4, 8) FSVC_CASE(6, 4) FSVC_CASE(6, 8)
 #undef FSVC_CASE
+  }
   // algorithmic work of this launch: 2*Cin*Cout*K*T flops; every operand tensor touched once
   const double BT = (double)c.B * a.T_out;
   const double flops = 2.0 * a.C_in * a.C_out * K * BT;
@@ -186,6 +229,7 @@ static ConvArgs conv_args(const Ctx& c, const ConvW& w, const float* in, int T_i
   a.out_cs = T_out;
   a.out_bs = (long long)w.C_out * T_out;
   a.slope = c.slope;
+  a.host_w = &w;
   return a;
 }
 
@@ -229,7 +273,7 @@ static void run_stage(Ctx& c, const StageW& w, const float* x, int T_in, int r, 
                       const float* beta, long long gb_bs, const float* spk_e, const StageBufs& sb, float* out) {
   const int C = w.first.C_out, T = T_in * r;
   const bool norm = spk_e != nullptr;
-  const int tile_len = conv_tile_len(T), n_tiles = (T + tile_len - 1) / tile_len;
+  const int tile_len = use_tc(c, w.d3) ? 32 : conv_tile_len(T), n_tiles = (T + tile_len - 1) / tile_len;
   auto film = [&](ConvArgs& a) {
     a.gamma = gamma;
     a.beta = beta;
@@ -305,7 +349,7 @@ static StageBufs alloc_stage_bufs(Arena& ar, int B, int C, int T_in, int T) {
   sb.x_ = ar.get<float>(n);
   sb.t2 = ar.get<float>(n);
   sb.t3 = sb.t1;  // t1 is dead once t2 exists
-  const int tile_len = conv_tile_len(T), n_tiles = (T + tile_len - 1) / tile_len;
+  const int n_tiles = (T + 31) / 32;  // finest statistics granularity of any kernel family
   sb.stats = ar.get<float2>((size_t)B * C * n_tiles);
   sb.pa = ar.get<float>((size_t)B * C);
   sb.pc = ar.get<float>((size_t)B * C);
@@ -323,6 +367,23 @@ static void repack(cudaStream_t s, const float* src, int C_out, int C_in, int K,
 static void bias_sum(cudaStream_t s, const float* a, const float* b, int n, float* dst, int off) {
   bias_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, n, dst, off);
 }
+
+static void pack_tc(cudaStream_t s, const ConvW& cw) {
+  const TcW& t = cw.tc;
+  const size_t total = t.elems() / 2;
+  const int blocks = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
+  pack_tc_weights_kernel<<<blocks, 256, 0, s>>>(cw.w, cw.C_in, cw.C_out, cw.K, t.CIB, t.n_blk, t.N_tile, t.n_ntiles,
+                                                (__nv_bfloat16*)t.w);
+}
+
+static int tc_setup_kernels() {
+  const int max_smem = 227 * 1024;
+  FSVC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  return FSVC_OK;
+}
+
+static bool mode_uses_tc(int mode) { return mode == FSVC_MODE_TC_BF16X3 || mode == FSVC_MODE_AUTO; }
 
 struct WS {  // full-forward workspace layout
   float* y[2][FSVC_MAX_STAGES];  // conditioning level outputs per branch
@@ -372,7 +433,7 @@ static const char* const lvl_sine_label[FSVC_MAX_STAGES] = {"l0.sine", "l1.sine"
 
 static int forward_fp32(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk,
                         float* out, int B, int frames, void* workspace, size_t ws_bytes, cudaStream_t stream,
-                        Profiler* prof = nullptr) {
+                        int mode, Profiler* prof = nullptr) {
   WS ws;
   const size_t need = layout_ws(h, B, frames, workspace, ws_bytes, &ws);
   if (need > ws_bytes) return fail(FSVC_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
@@ -382,6 +443,7 @@ static int forward_fp32(fsvc_handle* h, const float* ppg, const float* sine, con
   c.slope = h->cfg.lrelu_slope;
   c.eps = h->cfg.in_eps;
   c.prof = prof;
+  c.tc = mode_uses_tc(mode);
   if (prof) prof->mark(stream);
   const int n = h->n;
   const int T = frames * h->hop;
@@ -494,6 +556,7 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
     size_t bo = reserve(co);
     fix.push_back({&cw, wo});
     cw.b = (float*)bo;  // patched below
+    h->convs.push_back(&cw);
     if (info) add_info(prefix, (int64_t)co * ci * K, co);
   };
   std::vector<std::pair<float**, size_t>> fixp;
@@ -552,6 +615,28 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
     f.first->b = h->store + (size_t)f.first->b;
   }
   for (auto& f : fixp) *f.first = h->store + f.second;
+  // tensor-core weight copies
+  size_t tc_off = 0;
+  for (ConvW* cw : h->convs)
+    if (tc_plan(cw->C_in, cw->C_out, cw->K, &cw->tc)) {
+      cw->tc.w = (const __nv_bfloat16*)tc_off;  // offset, patched below
+      tc_off += (cw->tc.elems() + 127) & ~(size_t)127;
+    }
+  h->tc_elems = tc_off;
+  if (tc_off && cudaMalloc((void**)&h->tc_store, tc_off * sizeof(__nv_bfloat16)) != cudaSuccess) {
+    int rc = fail(FSVC_E_CUDA, "cudaMalloc(tc weights) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(h->store);
+    delete h;
+    return rc;
+  }
+  for (ConvW* cw : h->convs)
+    if (cw->tc.n_ntiles) cw->tc.w = h->tc_store + (size_t)cw->tc.w;
+  if (int rc = tc_setup_kernels()) {
+    cudaFree(h->store);
+    cudaFree(h->tc_store);
+    delete h;
+    return rc;
+  }
   *out = h;
   return FSVC_OK;
 }
@@ -559,6 +644,7 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
 void fsvc_destroy(fsvc_handle* h) {
   if (!h) return;
   if (h->store) cudaFree(h->store);
+  if (h->tc_store) cudaFree(h->tc_store);
   delete h;
 }
 
@@ -636,6 +722,8 @@ int fsvc_set_weights(fsvc_handle* h, const float* const* p, int n, void* stream_
   }
   put(h->last);
   if (k != n) return fail(FSVC_E_STATE, "internal: consumed %d of %d weight tensors", k, n);
+  for (ConvW* cw : h->convs)
+    if (cw->tc.w) pack_tc(s, *cw);
   FSVC_CUDA(cudaGetLastError());
   h->weights_set = true;
   return FSVC_OK;
@@ -666,7 +754,7 @@ int fsvc_forward(fsvc_handle* h, const float* ppg, const float* sine, const floa
     return fail(FSVC_E_INVALID, "spk given but the generator was built with use_spk_emb=0 (no emb_projector)");
   if (mode != FSVC_MODE_FP32 && mode != FSVC_MODE_TC_BF16X3 && mode != FSVC_MODE_AUTO)
     return fail(FSVC_E_INVALID, "unknown mode %d", mode);
-  return forward_fp32(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream);
+  return forward_fp32(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream, mode);
 }
 
 int fsvc_forward_profile(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk,
@@ -677,9 +765,9 @@ int fsvc_forward_profile(fsvc_handle* h, const float* ppg, const float* sine, co
   if (!ppg || !sine || !lft || !out || !workspace || !records || !count) return fail(FSVC_E_INVALID, "null pointer");
   if (!h->weights_set) return fail(FSVC_E_STATE, "fsvc_forward_profile called before fsvc_set_weights");
   if (spk && !h->cfg.use_spk_emb) return fail(FSVC_E_INVALID, "spk given but use_spk_emb=0");
-  (void)mode;
   Profiler prof;
-  rc = forward_fp32(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream, &prof);
+  rc = forward_fp32(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream, mode,
+                    &prof);
   if (rc == FSVC_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
     rc = fail(FSVC_E_CUDA, "stream synchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
   int n = 0;
@@ -739,9 +827,15 @@ static ConvW tmp_conv(Arena& ar, cudaStream_t s, const float* w, const float* b,
   cw.K = K;
   cw.w = ar.get<float>((size_t)co * ci * K);
   cw.b = ar.get<float>(co);
+  __nv_bfloat16* tw = nullptr;
+  if (tc_plan(ci, co, K, &cw.tc)) tw = ar.get<__nv_bfloat16>(cw.tc.elems());
   if (ar.ok()) {
     repack(s, w, co, ci, K, cw.w, co, 0, 0);
     bias_sum(s, b, nullptr, co, cw.b, 0);
+    if (tw) {
+      cw.tc.w = tw;
+      pack_tc(s, cw);
+    }
   }
   return cw;
 }
@@ -749,12 +843,13 @@ static ConvW tmp_conv(Arena& ar, cudaStream_t s, const float* w, const float* b,
 size_t fsvc_block_workspace_bytes(int B, int c_in, int c, int T_out) {
   if (B < 1 || c_in < 1 || c < 1 || T_out < 1) return 0;
   const size_t act = ((size_t)B * c * T_out * 4 + 255) & ~(size_t)255;
-  const size_t wts = 8 * (((size_t)c * (c_in > c ? c_in : c) * 3 * 4 + 255 + 1024) & ~(size_t)255);
+  const size_t cm = (size_t)((c_in > c ? c_in : c) + 64);
+  const size_t wts = 8 * ((((size_t)c + 64) * cm * 3 * (4 + 4 * 2) + 255 + 1024) & ~(size_t)255);
   return 10 * act + wts + (size_t)B * c * 4 * 4 + (1 << 16) + (size_t)B * c * (T_out / 128 + 2) * 8;
 }
 
 int fsvc_downsample_forward(const float* x, float* out, const float* const* w, int B, int c_in, int c, int T,
-                            int scale, float slope, void* workspace, size_t workspace_bytes, void* stream) {
+                            int scale, float slope, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   if (!x || !out || !w || !workspace) return fail(FSVC_E_INVALID, "null pointer");
   if (B < 1 || c_in < 1 || c < 1 || T < 1 || scale < 1) return fail(FSVC_E_INVALID, "bad shape");
   if (T % scale) return fail(FSVC_E_INVALID, "T (%d) must be divisible by the downsampling scale (%d)", T, scale);
@@ -770,13 +865,15 @@ int fsvc_downsample_forward(const float* x, float* out, const float* const* w, i
   ctx.B = B;
   ctx.slope = slope;
   ctx.eps = 0.f;
+  ctx.tc = mode_uses_tc(mode);
+  if (tc_setup_kernels()) return FSVC_E_CUDA;
   run_downsample(ctx, r1, c1, c2, c4, x, T, scale, tr, ta, tb, out);
   FSVC_CUDA(cudaGetLastError());
   return FSVC_OK;
 }
 
 int fsvc_film_forward(const float* x, float* scale, float* shift, const float* const* w, int B, int c, int T,
-                      float slope, void* workspace, size_t workspace_bytes, void* stream) {
+                      float slope, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   if (!x || !scale || !shift || !w || !workspace) return fail(FSVC_E_INVALID, "null pointer");
   if (B < 1 || c < 1 || T < 1) return fail(FSVC_E_INVALID, "bad shape");
   cudaStream_t s = (cudaStream_t)stream;
@@ -790,6 +887,8 @@ int fsvc_film_forward(const float* x, float* scale, float* shift, const float* c
   ctx.B = B;
   ctx.slope = slope;
   ctx.eps = 0.f;
+  ctx.tc = mode_uses_tc(mode);
+  if (tc_setup_kernels()) return FSVC_E_CUDA;
   ConvArgs a = conv_args(ctx, cv, x, T, T, 1, hbuf);
   a.post_lrelu = 1;
   launch_conv(ctx, a, 3);
@@ -812,7 +911,7 @@ __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict
 int fsvc_upsample_forward(const float* x, const float* s_scale, const float* s_shift, const float* l_scale,
                           const float* l_shift, const float* spk, float* out, const float* const* w, int B, int c_in,
                           int c, int T, int scale, int spk_emb_size, float slope, float eps, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+                          size_t workspace_bytes, int mode, void* stream) {
   if (!x || !s_scale || !s_shift || !l_scale || !l_shift || !out || !w || !workspace)
     return fail(FSVC_E_INVALID, "null pointer");
   if (B < 1 || c_in < 1 || c < 1 || T < 1 || scale < 1) return fail(FSVC_E_INVALID, "bad shape");
@@ -837,6 +936,8 @@ int fsvc_upsample_forward(const float* x, const float* s_scale, const float* s_s
   ctx.B = B;
   ctx.slope = slope;
   ctx.eps = eps;
+  ctx.tc = mode_uses_tc(mode);
+  if (tc_setup_kernels()) return FSVC_E_CUDA;
   add2_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(s_scale, l_scale, gamma, ne);
   add2_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(s_shift, l_shift, beta, ne);
   if (spk) spk_project_kernel<<<B, 256, 0, s>>>(spk, spk_emb_size, w[12], w[13], c, e);

@@ -51,6 +51,15 @@ class _Workspace:
         return self.buf
 
 
+def _block_mode(module):
+    """Precision mode of a standalone sub-block: attribute ``precision`` or $FSVC_MODE, default auto."""
+    name = getattr(module, "precision", None) or os.environ.get("FSVC_MODE", "auto")
+    try:
+        return abi.MODES[name]
+    except KeyError:
+        raise ValueError(f"precision must be one of {sorted(abi.MODES)}, got {name!r}")
+
+
 def _conv_wb(conv):
     return [_f32c(effective_weight(conv)), _f32c(conv.bias)]
 
@@ -107,7 +116,8 @@ class FastSVCUpsampleNet(nn.Module):
             abi.check(lib.fsvc_upsample_forward(
                 x.data_ptr(), s_scale.data_ptr(), s_shift.data_ptr(), l_scale.data_ptr(), l_shift.data_ptr(),
                 0 if spk_emb is None else spk_emb.data_ptr(), out.data_ptr(), abi.ptr_array(ptrs), B, c_in, c, T,
-                self._scale, spk_size, LRELU_SLOPE, IN_EPS, ws.data_ptr(), ws.numel(), _stream(x.device)))
+                self._scale, spk_size, LRELU_SLOPE, IN_EPS, ws.data_ptr(), ws.numel(), _block_mode(self),
+                _stream(x.device)))
         return out
 
 
@@ -143,7 +153,7 @@ class FastSVCDownsampleNet(nn.Module):
             ws = self._ws.get(lib.fsvc_block_workspace_bytes(B, c_in, c, T // self._scale), x.device)
             abi.check(lib.fsvc_downsample_forward(
                 x.data_ptr(), out.data_ptr(), abi.ptr_array([t.data_ptr() for t in w]), B, c_in, c, T, self._scale,
-                LRELU_SLOPE, ws.data_ptr(), ws.numel(), _stream(x.device)))
+                LRELU_SLOPE, ws.data_ptr(), ws.numel(), _block_mode(self), _stream(x.device)))
         return out
 
 
@@ -170,7 +180,7 @@ class FastSVCFiLMNet(nn.Module):
             ws = self._ws.get(lib.fsvc_block_workspace_bytes(B, c, c, T), x.device)
             abi.check(lib.fsvc_film_forward(
                 x.data_ptr(), scale.data_ptr(), shift.data_ptr(), abi.ptr_array([t.data_ptr() for t in w]), B, c, T,
-                LRELU_SLOPE, ws.data_ptr(), ws.numel(), _stream(x.device)))
+                LRELU_SLOPE, ws.data_ptr(), ws.numel(), _block_mode(self), _stream(x.device)))
         return scale, shift
 
 

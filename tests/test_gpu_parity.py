@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 # BASELINE.json north_star: waveform parity <= 1e-3 max-abs vs the reference fp32 generator.
 TOL = 1e-3
-MODES = ["fp32", "auto"]
+MODES = ["fp32", "tc_bf16x3", "auto"]
 
 
 def _cuda():
@@ -63,7 +63,8 @@ def test_generator_matches_oracle_on_fresh_inputs(precision, golden_index):
     assert np.abs(y - ref).max() <= TOL
 
 
-def test_blocks_match_reference_golden():
+@pytest.mark.parametrize("precision", ["fp32", "tc_bf16x3"])
+def test_blocks_match_reference_golden(precision):
     from harana.models.fastsvc import FastSVCDownsampleNet, FastSVCFiLMNet, FastSVCUpsampleNet
     from svcc23_fastsvc_b200 import synthetic as syn
     gold = load_golden("blocks")
@@ -72,6 +73,7 @@ def test_blocks_match_reference_golden():
     def load(mod, prefix):
         mod.load_state_dict({k[len(prefix) + 1:]: torch.from_numpy(v) for k, v in params.items()
                              if k.startswith(prefix + ".")})
+        mod.precision = precision
         return mod.eval().to(_cuda())
 
     d0 = load(FastSVCDownsampleNet(1, 24, 1), "downsampling_sine.0")
@@ -89,7 +91,7 @@ def test_blocks_match_reference_golden():
     for got, key in ((y0, "down0_out"), (y1, "down1_out"), (sc, "film0_scale"), (sh, "film0_shift"),
                      (yu, "up_out"), (yn, "up_out_nospk")):
         err = np.abs(got.cpu().numpy() - gold[key]).max()
-        assert err <= 1e-4, (key, err)
+        assert err <= (1e-4 if precision == "fp32" else 1e-3), (key, err)
     with pytest.raises(ValueError):
         d1(torch.zeros(1, 24, 23, device=_cuda()))  # T not divisible by the scale
 
@@ -168,6 +170,8 @@ def test_training_step_gradients_match_torch_graph():
     from svcc23_fastsvc_b200 import synthetic as syn
     cfg = dict(in_channels=16, mid_channels=[16, 8], upsampling_scales=[2, 3], out_channels=1, spk_emb_size=8,
                use_spk_emb=True)
+    torch.backends.cudnn.allow_tf32 = False     # the comparison graph must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     g = M.FastSVCGenerator(**cfg).to(_cuda())
     ppg, sine, lft, spk = syn.make_inputs(2, 6, cfg, seed=3)
     y = g(_t(ppg), _t(sine), _t(lft), _t(spk))
