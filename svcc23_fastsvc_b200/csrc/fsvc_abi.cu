@@ -11,6 +11,7 @@
 #include "../../include/fsvc.h"
 #include "conv_f32.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 
 namespace fsvc {
 
@@ -34,7 +35,9 @@ struct ConvW {  // packed [C_in][K][C_out] + bias[C_out], device
   float* w = nullptr;
   float* b = nullptr;
   int C_in = 0, C_out = 0, K = 0;
-  TcW tc;  // tensor-core copy of the same weights (tc.w == nullptr: conv not eligible)
+  TcW tc;   // tensor-core copy of the same weights (tc.w == nullptr: conv not eligible)
+  TcW tc2;  // copy tiled for the persistent channels-last kernel (conv_tc2.cuh)
+  int tc2_resident = 0;
 };
 
 // Tensor-core tiling of a conv: N tiles of <= 128 output channels (multiple of 16), input-channel
@@ -50,6 +53,38 @@ static bool tc_plan(int C_in, int C_out, int K, TcW* t) {
   t->n_blk = (c16 + 63) / 64;
   t->CIB = ((c16 + t->n_blk - 1) / t->n_blk + 15) / 16 * 16;
   t->K = K;
+  return true;
+}
+
+// Tiling of a conv for conv_tc2_kernel: ci blocks of <= 64 channels, N tiles of <= 128 output channels;
+// weights stay resident in shared memory when they fit next to the 2-deep A ring at the widest
+// dilation (27).  Independent of the batch size, so results never depend on it.
+static bool tc2_plan(int C_in, int C_out, int K, ConvW* cw) {
+  TcW* t = &cw->tc2;
+  if (C_out % 8 != 0 || C_in < 8) return false;
+  const int c16 = (C_in + 15) / 16 * 16;
+  t->n_blk = (c16 + 63) / 64;
+  t->CIB = ((c16 + t->n_blk - 1) / t->n_blk + 15) / 16 * 16;
+  const int n16 = (C_out + 15) / 16 * 16;
+  t->n_ntiles = (n16 + 127) / 128;
+  t->N_tile = ((n16 + t->n_ntiles - 1) / t->n_ntiles + 15) / 16 * 16;
+  t->N_alloc = 32;
+  while (t->N_alloc < t->N_tile) t->N_alloc *= 2;
+  t->K = K;
+  const size_t budget = (size_t)200 * 1024;
+  const int W_max = kTc2M + 2 * 27;
+  const size_t wbytes = (size_t)2 * K * t->CIB * t->n_blk * t->N_tile * 2;
+  const size_t abytes = (size_t)2 * (t->CIB / 8) * W_max * 16;
+  cw->tc2_resident = (wbytes + 2 * abytes + 4096 <= budget) ? 1 : 0;
+  if (!cw->tc2_resident) {
+    // streamed weights: the (N tile, ci block) chunk rides in the ring next to the A block
+    for (int cib = 64; cib >= 16; cib -= 16) {
+      t->CIB = cib;
+      t->n_blk = (c16 + cib - 1) / cib;
+      const size_t b_blk = (size_t)2 * K * cib * t->N_tile * 2, a_blk = (size_t)2 * (cib / 8) * W_max * 16;
+      if (2 * (b_blk + a_blk) + 4096 <= budget) break;
+    }
+  }
   return true;
 }
 
@@ -83,6 +118,8 @@ struct fsvc_handle {
   size_t store_floats = 0;
   __nv_bfloat16* tc_store = nullptr;  // tensor-core (bf16 hi/lo) copies of the conv weights
   size_t tc_elems = 0;
+  bool tc2_ok = false;                // every conv of the forward can run on conv_tc2_kernel
+  int num_sms = 148;
   std::vector<ConvW*> convs;          // every conv of the generator (for the tensor-core repack)
   StageW stage[FSVC_MAX_STAGES];
   LevelW level[FSVC_MAX_STAGES];
@@ -368,8 +405,7 @@ static void bias_sum(cudaStream_t s, const float* a, const float* b, int n, floa
   bias_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, b, n, dst, off);
 }
 
-static void pack_tc(cudaStream_t s, const ConvW& cw) {
-  const TcW& t = cw.tc;
+static void pack_tc(cudaStream_t s, const ConvW& cw, const TcW& t) {
   const size_t total = t.elems() / 2;
   const int blocks = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
   pack_tc_weights_kernel<<<blocks, 256, 0, s>>>(cw.w, cw.C_in, cw.C_out, cw.K, t.CIB, t.n_blk, t.N_tile, t.n_ntiles,
@@ -380,6 +416,8 @@ static int tc_setup_kernels() {
   const int max_smem = 227 * 1024;
   FSVC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return FSVC_OK;
 }
 
@@ -499,6 +537,317 @@ static int forward_fp32(fsvc_handle* h, const float* ppg, const float* sine, con
   FSVC_CUDA(cudaGetLastError());
   return FSVC_OK;
 }
+
+
+// ===========================================================================
+// tensor-core forward over channels-last activations (conv_tc2.cuh)
+// ===========================================================================
+struct WS2 {
+  float* y[2][FSVC_MAX_STAGES];  // [B][T_l][C_l] conditioning level outputs per branch
+  float* H[FSVC_MAX_STAGES];     // [B][T_l][2C] lrelu(film.conv(y)) of both branches, side by side
+  float* GB[FSVC_MAX_STAGES];    // [B][T_l][2C] gamma | beta (summed over branches)
+  float *tr[2], *ta[2], *tb[2];  // per-branch temporaries of a level chain
+  float* e[FSVC_MAX_STAGES];     // [B][C] projected speaker embedding per stage
+  float *h0[FSVC_MAX_STAGES], *xr[FSVC_MAX_STAGES], *t1[FSVC_MAX_STAGES], *x_[FSVC_MAX_STAGES],
+      *t2[FSVC_MAX_STAGES], *xs[FSVC_MAX_STAGES];
+  float2* stats;                 // [B][n_seg][C]
+  float *pa, *pc;                // [B][C]
+};
+
+static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, size_t cap, WS2* ws) {
+  Arena ar(base, cap);
+  const int n = h->n;
+  const int T = frames * h->hop;
+  int T_l = T;
+  size_t max_lvl = 0, max_stat = 0, max_bc = 0;
+  for (int l = 0; l < n; ++l) {
+    T_l /= h->dscale[l];
+    const size_t ne = (size_t)B * h->lvl_c[l] * T_l;
+    max_lvl = ne > max_lvl ? ne : max_lvl;
+    for (int br = 0; br < 2; ++br) ws->y[br][l] = ar.get<float>(ne);
+    ws->H[l] = ar.get<float>(2 * ne);
+    ws->GB[l] = ar.get<float>(2 * ne);
+  }
+  for (int br = 0; br < 2; ++br) {
+    ws->tr[br] = ar.get<float>(max_lvl);
+    ws->ta[br] = ar.get<float>(max_lvl);
+    ws->tb[br] = ar.get<float>(max_lvl);
+  }
+  int T_in = frames;
+  for (int i = 0; i < n; ++i) {
+    const int C = h->cfg.mid_channels[i], r = h->cfg.upsampling_scales[i];
+    const size_t ne = (size_t)B * C * T_in * r;
+    ws->e[i] = ar.get<float>((size_t)B * C);
+    ws->h0[i] = ar.get<float>((size_t)B * C * T_in);
+    ws->xr[i] = ar.get<float>(ne);
+    ws->t1[i] = ar.get<float>(ne);
+    ws->x_[i] = ar.get<float>(ne);
+    ws->t2[i] = ar.get<float>(ne);
+    ws->xs[i] = ar.get<float>(ne);
+    T_in *= r;
+    const size_t st = (size_t)B * C * ((T_in + 31) / 32);
+    max_stat = st > max_stat ? st : max_stat;
+    max_bc = (size_t)B * C > max_bc ? (size_t)B * C : max_bc;
+  }
+  ws->stats = ar.get<float2>(max_stat);
+  ws->pa = ar.get<float>(max_bc);
+  ws->pc = ar.get<float>(max_bc);
+  return ar.off;
+}
+
+// Fill the tiling / weight half of the arguments of one conv.
+static Tc2Args tc2_args(const Ctx& c, const ConvW& w, const float* in, int in_ld, int T_in, int T_out, int dil,
+                        float* out, int out_ld) {
+  Tc2Args a;
+  memset(&a, 0, sizeof(a));
+  a.in = in;
+  a.in_ld = in_ld;
+  a.T_in = T_in;
+  a.C_in = w.C_in;
+  a.up = 1;
+  a.down = 1;
+  a.w = w.tc2.w;
+  a.CIB = w.tc2.CIB;
+  a.n_blk = w.tc2.n_blk;
+  a.N_tile = w.tc2.N_tile;
+  a.n_ntiles = w.tc2.n_ntiles;
+  a.w_resident = w.tc2_resident;
+  a.bias = w.b;
+  a.dil = dil;
+  a.C_out = w.C_out;
+  a.T_out = T_out;
+  a.out = out;
+  a.out_ld = out_ld;
+  a.slope = c.slope;
+  return a;
+}
+
+// Launch 1 or 2 problems of identical tiling (same conv shape) as one persistent grid.
+static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, int n_prob, const char* name) {
+  Tc2Batch pb;
+  memset(&pb, 0, sizeof(pb));
+  for (int i = 0; i < n_prob; ++i) pb.p[i] = p[i];
+  pb.n_prob = n_prob;
+  pb.B = c.B;
+  pb.m_tiles = (p[0].T_out + kTc2M - 1) / kTc2M;
+  const int W = kTc2M + 2 * (K / 2) * p[0].dil;
+  const Tc2Smem L = tc2_smem_layout(K, p[0].CIB, p[0].n_blk, p[0].N_tile, p[0].w_resident, W, p[0].C_in);
+  int acc_stride = 32;
+  while (acc_stride < p[0].N_tile) acc_stride *= 2;
+  int per_sm = (int)((size_t)(227 * 1024) / ((size_t)L.total + 1024));
+  per_sm = per_sm < 1 ? 1 : per_sm;
+  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(256, 2)
+  if (per_sm * 2 * acc_stride > 512) per_sm = 512 / (2 * acc_stride);
+  const int groups = n_prob * p[0].n_ntiles;
+  const int items = c.B * pb.m_tiles;
+  int per_group = (h->num_sms * per_sm) / groups;
+  per_group = per_group < 1 ? 1 : per_group;
+  per_group = per_group > items ? items : per_group;
+  const dim3 grid(per_group * groups);
+  if (L.total > 227u * 1024u) {
+    c.err = 1;
+    return;
+  }
+  if (K == 3) conv_tc2_kernel<3><<<grid, kTc2Threads, L.total, c.stream>>>(pb);
+  else conv_tc2_kernel<1><<<grid, kTc2Threads, L.total, c.stream>>>(pb);
+  double flops = 0, elems = 0;
+  for (int i = 0; i < n_prob; ++i) {
+    const Tc2Args& a = p[i];
+    const double BT = (double)c.B * a.T_out;
+    flops += 2.0 * a.C_in * a.C_out * K * BT;
+    elems += a.gen_w ? BT : (double)c.B * a.C_in * ((double)a.T_out / a.up);
+    elems += BT * a.C_out * ((a.out ? 1 : 0) + (a.raw ? 1 : 0) + (a.res ? 1 : 0) + (a.gamma ? 2 : 0));
+    elems += (double)a.C_in * a.C_out * K;
+  }
+  c.launched(name, flops, 4.0 * elems);
+}
+
+static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk,
+                       float* out, int B, int frames, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                       Profiler* prof = nullptr) {
+  WS2 ws;
+  const size_t need = layout_ws2(h, B, frames, workspace, ws_bytes, &ws);
+  if (need > ws_bytes) return fail(FSVC_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  Ctx c;
+  c.stream = stream;
+  c.B = B;
+  c.slope = h->cfg.lrelu_slope;
+  c.eps = h->cfg.in_eps;
+  c.prof = prof;
+  if (prof) prof->mark(stream);
+  const int n = h->n;
+  const int T = frames * h->hop;
+  const int S = h->cfg.spk_emb_size;
+
+  if (spk) {  // every stage's emb_projector(normalize(spk)) in one launch                fastsvc.py:135-137
+    SpkProjArgs sp;
+    memset(&sp, 0, sizeof(sp));
+    for (int i = 0; i < n; ++i) {
+      sp.W[i] = h->stage[i].emb_w;
+      sp.bias[i] = h->stage[i].emb_b;
+      sp.e[i] = ws.e[i];
+      sp.C[i] = h->cfg.mid_channels[i];
+    }
+    spk_project_all_kernel<<<dim3(B, n), 256, 0, stream>>>(spk, S, sp);
+    c.label = "";
+    c.launched("spk_project", 0.0, 0.0);
+  }
+
+  // ---- conditioning chains, both branches per launch (fastsvc.py:180-193, 220-232) ----
+  int T_prev = T, T_l = T;
+  for (int l = 0; l < n; ++l) {
+    T_l = T_prev / h->dscale[l];
+    const LevelW& lw = h->level[l];
+    const int C = h->lvl_c[l];
+    c.label = lvl_label[l];
+    Tc2Args p[2];
+    if (lw.c1[0].C_in == 1) {
+      // 1-channel input: the first conv (and the 1x1 residual) are generated inside the consumers
+      for (int br = 0; br < 2; ++br) {
+        const float* sig = br == 0 ? lft : sine;
+        p[br] = tc2_args(c, lw.c2[br], sig, 1, T_prev, T_l, 2, ws.tb[br], C);
+        p[br].gen_w = lw.c1[br].w;
+        p[br].gen_b = lw.c1[br].b;
+        p[br].pre_lrelu = 1;
+        p[br].down = 1;
+      }
+      launch_tc2(c, h, 3, p, 2, "down_d1+d2");
+      for (int br = 0; br < 2; ++br) {
+        const float* sig = br == 0 ? lft : sine;
+        p[br] = tc2_args(c, lw.c4[br], ws.tb[br], C, T_l, T_l, 4, ws.y[br][l], C);
+        p[br].pre_lrelu = 1;
+        p[br].gres_w = lw.r1[br].w;
+        p[br].gres_b = lw.r1[br].b;
+        p[br].gres_x = sig;
+      }
+      launch_tc2(c, h, 3, p, 2, "down_d4+r");
+    } else {
+      const int Cp = h->lvl_c[l - 1];
+      for (int br = 0; br < 2; ++br) {
+        p[br] = tc2_args(c, lw.r1[br], ws.y[br][l - 1], Cp, T_prev, T_l, 1, ws.tr[br], C);
+        p[br].down = h->dscale[l];
+      }
+      launch_tc2(c, h, 1, p, 2, "down_r1x1");
+      for (int br = 0; br < 2; ++br) {
+        p[br] = tc2_args(c, lw.c1[br], ws.y[br][l - 1], Cp, T_prev, T_l, 1, ws.ta[br], C);
+        p[br].down = h->dscale[l];
+        p[br].pre_lrelu = 1;
+      }
+      launch_tc2(c, h, 3, p, 2, "down_d1");
+      for (int br = 0; br < 2; ++br) {
+        p[br] = tc2_args(c, lw.c2[br], ws.ta[br], C, T_l, T_l, 2, ws.tb[br], C);
+        p[br].pre_lrelu = 1;
+      }
+      launch_tc2(c, h, 3, p, 2, "down_d2");
+      for (int br = 0; br < 2; ++br) {
+        p[br] = tc2_args(c, lw.c4[br], ws.tb[br], C, T_l, T_l, 4, ws.y[br][l], C);
+        p[br].pre_lrelu = 1;
+        p[br].res = ws.tr[br];
+        p[br].res_ld = C;
+      }
+      launch_tc2(c, h, 3, p, 2, "down_d4");
+    }
+    for (int br = 0; br < 2; ++br) {
+      p[br] = tc2_args(c, lw.film[br], ws.y[br][l], C, T_l, T_l, 1, ws.H[l] + (size_t)br * C, 2 * C);
+      p[br].post_lrelu = 1;
+    }
+    launch_tc2(c, h, 3, p, 2, "film_conv");
+    p[0] = tc2_args(c, lw.film_out, ws.H[l], 2 * C, T_l, T_l, 1, ws.GB[l], 2 * C);
+    launch_tc2(c, h, 3, p, 1, "film_out");
+    T_prev = T_l;
+  }
+
+  // ---- upsampling stages (fastsvc.py:80-140) ----
+  const float* x = ppg;
+  int x_ld = 0, T_in = frames;
+  for (int i = 0; i < n; ++i) {
+    const StageW& w = h->stage[i];
+    const int C = h->cfg.mid_channels[i], r = h->cfg.upsampling_scales[i];
+    const int l = n - 1 - i, T_s = T_in * r, n_seg = (T_s + 31) / 32;
+    const float* gamma = ws.GB[l];
+    const float* beta = ws.GB[l] + C;
+    const bool norm = spk != nullptr;
+    c.label = stage_label[i];
+    auto film = [&](Tc2Args& a) {
+      a.gamma = gamma;
+      a.beta = beta;
+      a.gb_ld = 2 * C;
+      if (norm) {
+        a.stats = ws.stats;
+        a.n_seg = n_seg;
+      }
+    };
+    auto finalize = [&]() {
+      if (!norm) return;
+      in_finalize2_kernel<<<B * C, 64, 0, stream>>>(ws.stats, n_seg, T_s, C, ws.e[i], c.eps, ws.pa, ws.pc);
+      c.launched("in_finalize", 0.0, 8.0 * B * C * n_seg);
+    };
+    auto pre = [&](Tc2Args& a) {
+      if (norm) {
+        a.pre_a = ws.pa;
+        a.pre_c = ws.pc;
+      }
+      a.pre_lrelu = 1;
+    };
+    Tc2Args p[2];
+    // h0 = conv_first(x)                                                     fastsvc.py:93
+    p[0] = tc2_args(c, w.first, x, x_ld, T_in, T_in, 1, ws.h0[i], C);
+    p[0].in_nct = i == 0 ? 1 : 0;
+    launch_tc2(c, h, 3, p, 1, "conv_first");
+    // xr = Conv3(repeat_r(h0)) ; t1 = gamma*lrelu(Conv3(repeat_r(lrelu(h0)))) + beta   :94, :97-98
+    p[0] = tc2_args(c, w.res, ws.h0[i], C, T_in, T_s, 1, ws.xr[i], C);
+    p[0].up = r;
+    p[1] = tc2_args(c, w.up, ws.h0[i], C, T_in, T_s, 1, ws.t1[i], C);
+    p[1].up = r;
+    p[1].pre_lrelu = 1;
+    p[1].post_lrelu = 1;
+    film(p[1]);
+    launch_tc2(c, h, 3, p, 2, "residual+up_film");
+    finalize();
+    // x_ = Conv3_d3(lrelu(IN(t1)+e)) + xr ; t2 = gamma*x_ + beta            :99-105
+    p[0] = tc2_args(c, w.d3, ws.t1[i], C, T_s, T_s, 3, ws.t2[i], C);
+    pre(p[0]);
+    p[0].res = ws.xr[i];
+    p[0].res_ld = C;
+    p[0].raw = ws.x_[i];
+    p[0].raw_ld = C;
+    film(p[0]);
+    launch_tc2(c, h, 3, p, 1, "d3_film");
+    finalize();
+    // t3 = gamma * Conv3_d9(lrelu(IN(t2)+e)) + beta                         :106-107
+    p[0] = tc2_args(c, w.d9, ws.t2[i], C, T_s, T_s, 9, ws.t1[i], C);
+    pre(p[0]);
+    film(p[0]);
+    launch_tc2(c, h, 3, p, 1, "d9_film");
+    finalize();
+    // out = Conv3_d27(lrelu(IN(t3)+e)) + x_                                 :108-111
+    p[0] = tc2_args(c, w.d27, ws.t1[i], C, T_s, T_s, 27, ws.xs[i], C);
+    pre(p[0]);
+    p[0].res = ws.x_[i];
+    p[0].res_ld = C;
+    launch_tc2(c, h, 3, p, 1, "d27_skip");
+    x = ws.xs[i];
+    x_ld = C;
+    T_in = T_s;
+  }
+  // conv_last (1x1)                                                         fastsvc.py:330
+  {
+    const long long BT = (long long)B * T;
+    const int C = h->cfg.mid_channels[n - 1];
+    conv_last_ntc_kernel<<<(unsigned)((BT + 255) / 256), 256, 0, stream>>>(x, C, T, BT, h->last.w, h->last.b,
+                                                                          h->cfg.out_channels, out);
+    c.label = "";
+    c.launched("conv_last", 2.0 * BT * C * h->cfg.out_channels, 4.0 * BT * (C + h->cfg.out_channels));
+  }
+  h->launches = c.launches;
+  if (c.err) return fail(FSVC_E_INVALID, "internal: a conv tile does not fit in shared memory");
+  FSVC_CUDA(cudaGetLastError());
+  return FSVC_OK;
+}
+
+// AUTO / TC_BF16X3 run the channels-last tensor-core forward when the configuration allows it (every
+// mid channel count a multiple of 8); otherwise TC_BF16X3 uses the per-layer tcgen05 kernel and AUTO fp32.
+static bool use_tc2(const fsvc_handle* h, int mode) { return mode != FSVC_MODE_FP32 && h->tc2_ok; }
 
 }  // namespace fsvc
 
@@ -622,6 +971,25 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
       cw->tc.w = (const __nv_bfloat16*)tc_off;  // offset, patched below
       tc_off += (cw->tc.elems() + 127) & ~(size_t)127;
     }
+  // copies tiled for the channels-last persistent kernel; the forward is eligible when every conv
+  // except the 1-channel ones (level-0 first conv / 1x1 residual: generated in-kernel) and conv_last has one
+  h->tc2_ok = true;
+  for (ConvW* cw : h->convs) {
+    const bool tiny = (cw->C_in == 1) || cw == &h->last;
+    if (tiny) continue;
+    if (tc2_plan(cw->C_in, cw->C_out, cw->K, cw)) {
+      cw->tc2.w = (const __nv_bfloat16*)tc_off;
+      tc_off += (cw->tc2.elems() + 127) & ~(size_t)127;
+    } else {
+      h->tc2_ok = false;
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    if (cfg->mid_channels[i] % 8 != 0) h->tc2_ok = false;
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  }
   h->tc_elems = tc_off;
   if (tc_off && cudaMalloc((void**)&h->tc_store, tc_off * sizeof(__nv_bfloat16)) != cudaSuccess) {
     int rc = fail(FSVC_E_CUDA, "cudaMalloc(tc weights) failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -629,8 +997,10 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
     delete h;
     return rc;
   }
-  for (ConvW* cw : h->convs)
+  for (ConvW* cw : h->convs) {
     if (cw->tc.n_ntiles) cw->tc.w = h->tc_store + (size_t)cw->tc.w;
+    if (cw->tc2.n_ntiles) cw->tc2.w = h->tc_store + (size_t)cw->tc2.w;
+  }
   if (int rc = tc_setup_kernels()) {
     cudaFree(h->store);
     cudaFree(h->tc_store);
@@ -723,7 +1093,10 @@ int fsvc_set_weights(fsvc_handle* h, const float* const* p, int n, void* stream_
   put(h->last);
   if (k != n) return fail(FSVC_E_STATE, "internal: consumed %d of %d weight tensors", k, n);
   for (ConvW* cw : h->convs)
-    if (cw->tc.w) pack_tc(s, *cw);
+  {
+    if (cw->tc.w) pack_tc(s, *cw, cw->tc);
+    if (cw->tc2.w) pack_tc(s, *cw, cw->tc2);
+  }
   FSVC_CUDA(cudaGetLastError());
   h->weights_set = true;
   return FSVC_OK;
@@ -738,8 +1111,11 @@ static int check_shape(const fsvc_handle* h, int B, int frames) {
 }
 
 size_t fsvc_workspace_bytes(const fsvc_handle* h, int B, int frames, int mode) {
-  (void)mode;
   if (check_shape(h, B, frames) != FSVC_OK) return 0;
+  if (use_tc2(h, mode)) {
+    WS2 ws2;
+    return layout_ws2(h, B, frames, nullptr, 0, &ws2);
+  }
   WS ws;
   return layout_ws(h, B, frames, nullptr, 0, &ws);
 }
@@ -754,6 +1130,8 @@ int fsvc_forward(fsvc_handle* h, const float* ppg, const float* sine, const floa
     return fail(FSVC_E_INVALID, "spk given but the generator was built with use_spk_emb=0 (no emb_projector)");
   if (mode != FSVC_MODE_FP32 && mode != FSVC_MODE_TC_BF16X3 && mode != FSVC_MODE_AUTO)
     return fail(FSVC_E_INVALID, "unknown mode %d", mode);
+  if (use_tc2(h, mode))
+    return forward_tc2(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream);
   return forward_fp32(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream, mode);
 }
 
@@ -766,8 +1144,11 @@ int fsvc_forward_profile(fsvc_handle* h, const float* ppg, const float* sine, co
   if (!h->weights_set) return fail(FSVC_E_STATE, "fsvc_forward_profile called before fsvc_set_weights");
   if (spk && !h->cfg.use_spk_emb) return fail(FSVC_E_INVALID, "spk given but use_spk_emb=0");
   Profiler prof;
-  rc = forward_fp32(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream, mode,
-                    &prof);
+  if (use_tc2(h, mode))
+    rc = forward_tc2(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream, &prof);
+  else
+    rc = forward_fp32(h, ppg, sine, lft, spk, out, B, frames, workspace, workspace_bytes, (cudaStream_t)stream, mode,
+                      &prof);
   if (rc == FSVC_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
     rc = fail(FSVC_E_CUDA, "stream synchronize failed: %s", cudaGetErrorString(cudaGetLastError()));
   int n = 0;
@@ -834,7 +1215,7 @@ static ConvW tmp_conv(Arena& ar, cudaStream_t s, const float* w, const float* b,
     bias_sum(s, b, nullptr, co, cw.b, 0);
     if (tw) {
       cw.tc.w = tw;
-      pack_tc(s, cw);
+      pack_tc(s, cw, cw.tc);
     }
   }
   return cw;
