@@ -183,123 +183,200 @@ __device__ __forceinline__ void tc2_stage_a(const Tc2Args& a, int b, int t0, int
     }
     return;
   }
+  // channels-last fast path: the loads of up to 4 items per thread are all issued before the first is consumed
   const float* in_b = a.in + (long long)b * a.T_in * a.in_ld;
-  for (int idx = tid; idx < items; idx += kTc2Threads) {
-    const int r = idx / Gb, g = idx - r * Gb;
-    const int u = t0 - halo + r, c = ci0 + g * 8;
-    float v[8];
+  const uint32_t gb_magic = 0xFFFFFFFFu / (uint32_t)Gb + 1u;    // exact quotients for idx < 2^16
+  const uint32_t up_magic = 0xFFFFFFFFu / (uint32_t)a.up + 1u;  // (unused when up == 1)
+  constexpr int CH = 4;
+  for (int base = tid; base < items; base += CH * kTc2Threads) {
+    float4 q[CH][2];
+    bool live[CH];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (u >= 0 && u < a.T_out && c < a.C_in) {
-      const int src = (u / a.up) * a.down;
-      const float4* p = reinterpret_cast<const float4*>(in_b + (long long)src * a.in_ld + c);
-      const float4 q0 = __ldg(p), q1 = __ldg(p + 1);
-      v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
-      v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-      if (a.pre_a) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_pa[c + e], s_pc[c + e]);
-      }
-      if (a.pre_lrelu) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = lrelu(v[e], a.slope);
+    for (int j = 0; j < CH; ++j) {
+      const int idx = base + j * kTc2Threads;
+      live[j] = false;
+      q[j][0] = q[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < items) {
+        const int r = (int)__umulhi((uint32_t)idx, gb_magic), g = idx - r * Gb;
+        const int u = t0 - halo + r, c = ci0 + g * 8;
+        if (u >= 0 && u < a.T_out && c < a.C_in) {
+          const int src = (a.up == 1 ? u : (int)__umulhi((uint32_t)u, up_magic)) * a.down;
+          const float4* p = reinterpret_cast<const float4*>(in_b + (long long)src * a.in_ld + c);
+          q[j][0] = __ldg(p);
+          q[j][1] = __ldg(p + 1);
+          live[j] = true;
+        }
       }
     }
-    split_store(sA + (size_t)g * strip + (size_t)r * 16, plane, v);
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      const int idx = base + j * kTc2Threads;
+      if (idx < items) {
+        const int r = (int)__umulhi((uint32_t)idx, gb_magic), g = idx - r * Gb;
+        const int c = ci0 + g * 8;
+        float v[8] = {q[j][0].x, q[j][0].y, q[j][0].z, q[j][0].w, q[j][1].x, q[j][1].y, q[j][1].z, q[j][1].w};
+        if (live[j]) {
+          if (a.pre_a) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], s_pa[c + e], s_pc[c + e]);
+          }
+          if (a.pre_lrelu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = lrelu(v[e], a.slope);
+          }
+        }
+        split_store(sA + (size_t)g * strip + (size_t)r * 16, plane, v);
+      }
+    }
   }
+}
+
+// Sum over the 32 lanes of 16 per-lane values with 16 shuffles: lane L ends up with the total of value (L >> 1).
+__device__ __forceinline__ float warp_reduce16(const float (&x)[16], int lane) {
+  float y8[8], y4[4], y2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float send = b4 ? x[j] : x[j + 8], keep = b4 ? x[j + 8] : x[j];
+    y8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float send = b3 ? y8[j] : y8[j + 4], keep = b3 ? y8[j + 4] : y8[j];
+    y4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const float send = b2 ? y4[j] : y4[j + 2], keep = b2 ? y4[j + 2] : y4[j];
+    y2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = b1 ? y2[0] : y2[1], keep = b1 ? y2[1] : y2[0];
+  float y = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  y += __shfl_xor_sync(0xffffffffu, y, 1);
+  return y;
 }
 
 // Epilogue of one finished tile: TMEM -> registers -> fused elementwise -> global (NTC rows).
 // Warp w owns TMEM lanes 32*(w%4).. (= time rows) and half (w/4) of the tile's valid output channels.
-__device__ __forceinline__ void tc2_epilogue(const Tc2Args& a, int b, int t0, int nt, uint32_t tmem_acc, int warp,
-                                             int lane) {
+// The residual / FiLM operands of the first 12-channel pass are fetched by tc2_epi_prefetch, which the
+// kernel calls a whole staging phase earlier so their latency is hidden.
+struct Tc2EpiPre {
+  float4 rs[3], ga[3], be[3];
+  float gx;
+};
+struct Tc2EpiPos {
+  int t, cb, half, co_tile;
+  long long row;
+  bool ok;
+};
+__device__ __forceinline__ Tc2EpiPos tc2_epi_pos(const Tc2Args& a, int b, int t0, int nt, int warp, int lane) {
+  Tc2EpiPos p;
   const int q = warp & 3, h = warp >> 2;
-  const int t = t0 + q * 32 + lane;
-  const bool ok = t < a.T_out;
-  const int co_tile = nt * a.N_tile;
-  const int nvalid = min(a.N_tile, a.C_out - co_tile);
-  const int half = nvalid >> 1;       // multiple of 4 (C_out % 8 == 0)
-  const int cb = h * half;            // first column of this thread inside the N tile
-  const long long row = (long long)b * a.T_out + t;
+  p.t = t0 + q * 32 + lane;
+  p.ok = p.t < a.T_out;
+  p.co_tile = nt * a.N_tile;
+  const int nvalid = min(a.N_tile, a.C_out - p.co_tile);
+  p.half = nvalid >> 1;  // multiple of 4 (C_out % 8 == 0)
+  p.cb = h * p.half;     // first column of this thread inside the N tile
+  p.row = (long long)b * a.T_out + p.t;
+  return p;
+}
+__device__ __forceinline__ void tc2_epi_load(const Tc2Args& a, const Tc2EpiPos& p, int c0, Tc2EpiPre& e) {
+  const int n4 = min(3, (p.half - c0) >> 2);
+  const int co = p.co_tile + p.cb + c0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j < n4 && p.ok) {
+      if (a.res) e.rs[j] = __ldg(reinterpret_cast<const float4*>(a.res + p.row * a.res_ld + co) + j);
+      if (a.gamma) {
+        e.ga[j] = __ldg(reinterpret_cast<const float4*>(a.gamma + p.row * a.gb_ld + co) + j);
+        e.be[j] = __ldg(reinterpret_cast<const float4*>(a.beta + p.row * a.gb_ld + co) + j);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tc2_epi_prefetch(const Tc2Args& a, int b, int t0, int nt, int warp, int lane,
+                                                 Tc2EpiPre& e) {
+  const Tc2EpiPos p = tc2_epi_pos(a, b, t0, nt, warp, lane);
+  e.gx = 0.f;
+  if (a.gres_w && p.ok) e.gx = __ldg(a.gres_x + p.row);
+  tc2_epi_load(a, p, 0, e);
+}
+
+__device__ __forceinline__ void tc2_epilogue(const Tc2Args& a, int b, int t0, int nt, uint32_t tmem_acc, int warp,
+                                             int lane, Tc2EpiPre& pre) {
+  const Tc2EpiPos p = tc2_epi_pos(a, b, t0, nt, warp, lane);
+  const int q = warp & 3;
+  const bool ok = p.ok;
   const int n_rows_seg = min(32, a.T_out - (t0 + q * 32));  // valid rows of this warp's segment (may be <= 0)
   const int seg = (t0 >> 5) + q;
-  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb;
-  float gx = 0.f;
-  if (a.gres_w && ok) gx = __ldg(a.gres_x + row);
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)p.cb;
+  const float gx = pre.gx;
 
-  for (int c0 = 0; c0 < half; c0 += 12) {
-    const int n4 = min(3, (half - c0) >> 2);
-    float v[12], rs[12], ga[12], be[12];
+  for (int c0 = 0; c0 < p.half; c0 += 12) {
+    const int n4 = min(3, (p.half - c0) >> 2);
+    float v[16];
 #pragma unroll
     for (int j = 0; j < 3; ++j)
       if (j < n4) tmem_ld4_nowait(taddr + (uint32_t)(c0 + 4 * j), v + 4 * j);
-    const int co = co_tile + cb + c0;  // first global output channel of this pass
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      if (j < n4 && ok) {
-        if (a.res) {
-          const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.res + row * a.res_ld + co) + j);
-          rs[4 * j] = r4.x; rs[4 * j + 1] = r4.y; rs[4 * j + 2] = r4.z; rs[4 * j + 3] = r4.w;
-        }
-        if (a.gamma) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + row * a.gb_ld + co) + j);
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta + row * a.gb_ld + co) + j);
-          ga[4 * j] = g4.x; ga[4 * j + 1] = g4.y; ga[4 * j + 2] = g4.z; ga[4 * j + 3] = g4.w;
-          be[4 * j] = b4.x; be[4 * j + 1] = b4.y; be[4 * j + 2] = b4.z; be[4 * j + 3] = b4.w;
-        }
-      }
-    }
+    const int co = p.co_tile + p.cb + c0;  // first global output channel of this pass
+    if (c0 > 0) tc2_epi_load(a, p, c0, pre);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       if (j < n4) {
+        const float rs[4] = {pre.rs[j].x, pre.rs[j].y, pre.rs[j].z, pre.rs[j].w};
+        const float ga[4] = {pre.ga[j].x, pre.ga[j].y, pre.ga[j].z, pre.ga[j].w};
+        const float be[4] = {pre.be[j].x, pre.be[j].y, pre.be[j].z, pre.be[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = 4 * j + e;
           float x = v[i] + __ldg(a.bias + co + i);
-          if (a.res) x += ok ? rs[i] : 0.f;
+          if (a.res) x += ok ? rs[e] : 0.f;
           if (a.gres_w) x += fmaf(__ldg(a.gres_w + co + i), gx, __ldg(a.gres_b + co + i));
           v[i] = x;
         }
         if (a.raw && ok)
-          reinterpret_cast<float4*>(a.raw + row * a.raw_ld + co)[j] =
+          reinterpret_cast<float4*>(a.raw + p.row * a.raw_ld + co)[j] =
               make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = 4 * j + e;
           float x = v[i];
           if (a.post_lrelu) x = lrelu(x, a.slope);
-          if (a.gamma) x = ok ? fmaf(ga[i], x, be[i]) : 0.f;
+          if (a.gamma) x = ok ? fmaf(ga[e], x, be[e]) : 0.f;
           v[i] = x;
         }
         if (a.out && ok)
-          reinterpret_cast<float4*>(a.out + row * a.out_ld + co)[j] =
+          reinterpret_cast<float4*>(a.out + p.row * a.out_ld + co)[j] =
               make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       }
     }
     if (a.stats && n_rows_seg > 0) {
-      // per-channel (mean, M2) over the <= 32 rows of this warp, shifted by the segment's first
-      // sample so that the one-pass sums do not cancel (merged in double by in_finalize2_kernel)
-      float keep_mean = 0.f, keep_m2 = 0.f;
-      const float inv_n = 1.f / (float)n_rows_seg;
+      // per-channel (mean, M2) over the <= 32 rows of this warp.  One-pass sums of the deviations from
+      // the segment's first sample (no cancellation), reduced across the lanes with a transposing
+      // butterfly (44 shuffles per 12 channels); merged over segments in double by in_finalize2_kernel.
       const int nc = 4 * n4;
+      float d1[16], d2[16];
+      float my_piv = 0.f;
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        if (i >= nc) continue;  // warp-uniform
-        const float piv = __shfl_sync(0xffffffffu, v[i], 0);
-        const float d = ok ? v[i] - piv : 0.f;
-        float s1 = d, s2 = d * d;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        if (lane == i) {
-          keep_mean = piv + s1 * inv_n;
-          keep_m2 = fmaxf(s2 - s1 * s1 * inv_n, 0.f);
+      for (int i = 0; i < 16; ++i) {
+        d1[i] = 0.f;
+        d2[i] = 0.f;
+        if (i < 12 && i < nc) {
+          const float piv = __shfl_sync(0xffffffffu, v[i], 0);
+          const float d = ok ? v[i] - piv : 0.f;
+          d1[i] = d;
+          d2[i] = d * d;
+          if ((lane >> 1) == i) my_piv = piv;
         }
       }
-      if (lane < nc) a.stats[((long long)b * a.n_seg + seg) * a.C_out + co + lane] = make_float2(keep_mean, keep_m2);
+      const float s1 = warp_reduce16(d1, lane), s2 = warp_reduce16(d2, lane);
+      const float inv_n = 1.f / (float)n_rows_seg;
+      const int ch = lane >> 1;
+      if ((lane & 1) == 0 && ch < nc)
+        a.stats[((long long)b * a.n_seg + seg) * a.C_out + co + ch] =
+            make_float2(my_piv + s1 * inv_n, fmaxf(s2 - s1 * s1 * inv_n, 0.f));
     }
   }
 }
@@ -334,14 +411,10 @@ __host__ __device__ inline Tc2Smem tc2_smem_layout(int K, int CIB, int n_blk, in
   return s;
 }
 
-// grid = multiple of n_prob * n_ntiles; block = 256; dynamic smem = tc2_smem_layout().total
 template <int K>
-__global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_constant__ Tc2Batch pb) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+__device__ __forceinline__ void tc2_body(const Tc2Args& a, const Tc2Batch& pb, uint8_t* smem_raw) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // static work assignment: problem, N tile, then (b, time tile) round-robin
-  const int prob = blockIdx.x % pb.n_prob;
-  const Tc2Args& a = pb.p[prob];
+  // static work assignment: N tile, then (b, time tile) round-robin
   const int rest = blockIdx.x / pb.n_prob;
   const int nt = rest % a.n_ntiles;
   const int first = rest / a.n_ntiles;
@@ -388,7 +461,7 @@ __global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_c
   const uint32_t strip = (uint32_t)W * 16u, a_plane = Gb * strip;
   const uint32_t b_strip = (uint32_t)a.N_tile * 16u, b_half = (uint32_t)K * Gb * b_strip;
 
-  uint32_t ring_uses[2] = {0, 0};  // completed fills of A/B ring slot s
+  uint32_t ring_uses0 = 0, ring_uses1 = 0;  // completed fills of A/B ring slot 0 / 1
   uint32_t ring_pos = 0;
   int it = 0;
   int pb_b = 0, pb_t0 = 0;  // previous tile (epilogue pending)
@@ -405,15 +478,18 @@ __global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_c
     const uint32_t acc = (uint32_t)(it & 1);
     for (int blk = 0; blk < a.n_blk; ++blk, ++ring_pos) {
       const uint32_t s = ring_pos & 1u;
-      if (ring_uses[s] > 0) mbar_wait2(a_empty + s, (ring_uses[s] - 1) & 1u);
-      uint8_t* sA = smem_raw + L.a_off[s];
-      uint8_t* sB = a.w_resident ? sW + (size_t)blk * L.b_blk_bytes : smem_raw + L.b_off[s];
+      const uint32_t uses = s ? ring_uses1 : ring_uses0;
+      if (uses > 0) mbar_wait2(a_empty + s, (uses - 1) & 1u);
+      uint8_t* sA = smem_raw + L.a_off[0] + s * L.a_bytes;
+      uint8_t* sB = a.w_resident ? sW + (size_t)blk * L.b_blk_bytes : smem_raw + L.b_off[0] + s * L.b_blk_bytes;
       if (!a.w_resident && tid == 0) {
         mbar_expect_tx(b_full + s, L.b_blk_bytes);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(w_nt) + (size_t)blk * L.b_blk_bytes;
         for (uint32_t o = 0; o < L.b_blk_bytes; o += 32768u)
           bulk_g2s(sB + o, src + o, min(32768u, L.b_blk_bytes - o), b_full + s);
       }
+      Tc2EpiPre pre;
+      if (blk == 0 && it > 0) tc2_epi_prefetch(a, pb_b, pb_t0, nt, warp, lane, pre);
       tc2_stage_a(a, b, t0, blk, halo, W, sA, s_pa, s_pc, tid);
       fence_proxy_async();
       tc_fence_before();
@@ -423,7 +499,7 @@ __global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_c
           mbar_wait2(w_full, 0);
           w_ready = true;
         }
-        if (!a.w_resident) mbar_wait2(b_full + s, ring_uses[s] & 1u);
+        if (!a.w_resident) mbar_wait2(b_full + s, uses & 1u);
         tc_fence_after();
         const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
         const uint32_t d_tmem = tmem + acc * acc_stride;
@@ -445,13 +521,14 @@ __global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_c
         umma_commit(a_empty + s);
         if (blk == a.n_blk - 1) umma_commit(acc_full + acc);
       }
-      ring_uses[s]++;
+      if (s) ring_uses1++;
+      else ring_uses0++;
       if (blk == 0 && it > 0) {
         // drain the previous tile while the tensor core works on this one
         const uint32_t pacc = (uint32_t)((it - 1) & 1);
         mbar_wait2(acc_full + pacc, (uint32_t)(((it - 1) >> 1) & 1));
         tc_fence_after();
-        tc2_epilogue(a, pb_b, pb_t0, nt, tmem + pacc * acc_stride, warp, lane);
+        tc2_epilogue(a, pb_b, pb_t0, nt, tmem + pacc * acc_stride, warp, lane, pre);
         tc_fence_before();
       }
     }
@@ -462,12 +539,23 @@ __global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_c
     const uint32_t pacc = (uint32_t)((it - 1) & 1);
     mbar_wait2(acc_full + pacc, (uint32_t)(((it - 1) >> 1) & 1));
     tc_fence_after();
-    tc2_epilogue(a, pb_b, pb_t0, nt, tmem + pacc * acc_stride, warp, lane);
+    Tc2EpiPre pre;
+    tc2_epi_prefetch(a, pb_b, pb_t0, nt, warp, lane, pre);
+    tc2_epilogue(a, pb_b, pb_t0, nt, tmem + pacc * acc_stride, warp, lane, pre);
     tc_fence_before();
   }
   if (!w_ready && tid == 0) mbar_wait2(w_full, 0);  // never exit with a bulk copy in flight
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 2 * acc_stride);
+}
+
+// grid = multiple of n_prob * n_ntiles; block = 256; dynamic smem = tc2_smem_layout().total.
+// The two problems get their own copy of the body so that every argument is a constant-bank operand.
+template <int K>
+__global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_constant__ Tc2Batch pb) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  if (pb.n_prob == 1 || (blockIdx.x & 1) == 0) tc2_body<K>(pb.p[0], pb, smem_raw);
+  else tc2_body<K>(pb.p[1], pb, smem_raw);
 }
 
 // ---- small companions -------------------------------------------------------------------

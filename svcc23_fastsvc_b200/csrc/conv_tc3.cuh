@@ -1,0 +1,533 @@
+// Warp-specialised, software-pipelined tcgen05 1-D convolution over channels-last activations.
+//
+// Same contract as conv_tc2_kernel (Tc2Args: fused prologue / epilogue of every FastSVC conv), organised
+// as a four-role pipeline so that no role ever waits on HBM with nothing else to do:
+//
+//   warp 0      WEIGHTS    cp.async.bulk (UBLKCP) of the packed bf16 hi|lo weights: once when they fit in
+//                          shared memory, else one (N tile, ci block) chunk per MMA block through a 2-slot ring
+//   warp 1      MMA        one thread issues tcgen05.mma (bf16 3-term split, fp32 accumulation in TMEM,
+//                          two accumulators so tile i+1 is computed while tile i is drained)
+//   warps 2-5   TRANSFORM  128-bit loads of the A window, issued one 512-item chunk AHEAD of their use
+//                          (register double buffer) -> InstanceNorm affine -> LeakyReLU -> zero padding
+//                          -> bf16 hi|lo in the UMMA K-major canonical layout (taps = descriptor row shifts)
+//   warps 6-13  EPILOGUE   TMEM -> registers (+bias, residual, FiLM affine) -> 128-bit row stores; the
+//                          residual / gamma / beta rows of the NEXT sub-tile are requested before the
+//                          current one is waited for; InstanceNorm partial statistics through a per-warp
+//                          shared-memory transpose
+//
+// The roles meet only through mbarriers (full/empty pairs per ring slot, tcgen05.commit on the tensor-core
+// side).  One CTA per SM, a static round-robin list of (utterance, 128-step tile) items per CTA.
+// Activations are [B][T][C] fp32: every global access is a 128-bit access to a contiguous row segment.
+#pragma once
+#include "conv_tc2.cuh"
+
+namespace fsvc {
+
+constexpr int kTc3Threads = 448;
+constexpr int kTc3XformThreads = 128;  // warps 2..5
+constexpr int kTc3EpiThreads = 256;    // warps 6..13
+constexpr int kTc3ChunkItems = 4;      // 16-byte-chunk items per transform thread and prefetch chunk
+
+struct Tc3Cfg {
+  int n_prob;  // 1 or 2 problems (blockIdx.x % n_prob); problem 1 = problem 0 + the pointer deltas below
+  int B, m_tiles;
+  int nsub;       // epilogue sub-tile width (channels, multiple of 8, <= 32)
+  int a_slots;    // depth of the A ring (1..3)
+  int scr_pitch;  // floats per row of the per-warp statistics scratch (12 or 20)
+  uint32_t a_bytes, b_bytes;  // per ring slot
+  uint32_t off_w, off_a, off_b, off_scr, off_pa, off_bar, total;
+};
+
+struct Tc3Launch {
+  Tc2Args a;
+  long long d_in, d_w, d_bias, d_gen_w, d_gen_b, d_res, d_gres_w, d_gres_b, d_gres_x, d_raw, d_out;  // elements
+  Tc3Cfg c;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+enum {  // mbarrier indices
+  kBarBFull = 0,     // [2] streamed weight block landed
+  kBarBEmpty = 2,    // [2] MMAs that read it completed
+  kBarAFull = 4,     // [3] A block converted
+  kBarAEmpty = 7,    // [3] MMAs that read it completed
+  kBarAccFull = 10,  // [2] accumulator holds a finished tile
+  kBarAccEmpty = 12, // [2] epilogue drained it
+  kBarWFull = 14,    // resident weights landed
+  kBarCount = 15
+};
+
+// Shared-memory plan of one launch.  Returns false when even a 1-deep A ring does not fit.
+__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c) {
+  const int halo = (K / 2) * a.dil, W = kTc2M + 2 * halo;
+  const uint32_t Gb = a.CIB / 8;
+  c->a_bytes = 2u * Gb * W * 16u;
+  c->b_bytes = 2u * K * Gb * a.N_tile * 16u;
+  const int nvalid_max = a.C_out < a.N_tile ? a.C_out : a.N_tile;
+  int nsub = 8;
+  for (int cand : {24, 32, 16, 8})
+    if (nvalid_max % cand == 0) {
+      nsub = cand;
+      break;
+    }
+  c->nsub = nsub;
+  c->scr_pitch = nsub / 2 <= 12 ? 12 : 20;
+  const uint32_t w_bytes = a.w_resident ? c->b_bytes * a.n_blk : 0u;
+  const uint32_t scr_bytes = 8u * 32u * c->scr_pitch * 4u;
+  const uint32_t pa_bytes = 2u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;
+  for (int slots = 3; slots >= 1; --slots) {
+    c->a_slots = slots;
+    uint32_t off = 0;
+    c->off_w = off;
+    off += w_bytes;
+    c->off_a = off;
+    off += slots * c->a_bytes;
+    c->off_b = off;
+    off += a.w_resident ? 0u : 2u * c->b_bytes;
+    c->off_scr = off;
+    off += scr_bytes;
+    c->off_pa = off;
+    off += pa_bytes;
+    off = (off + 15u) & ~15u;
+    c->off_bar = off;
+    off += kBarCount * 8 + 16;
+    c->total = off;
+    if (off <= 227u * 1024u) return true;
+  }
+  return false;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* const smem = smem_raw;
+  const Tc2Args& a = L.a;
+  const Tc3Cfg& c = L.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int prob = blockIdx.x % c.n_prob;
+  const int rest = blockIdx.x / c.n_prob;
+  const int nt = rest % a.n_ntiles;
+  const int first = rest / a.n_ntiles;
+  const int step = gridDim.x / (c.n_prob * a.n_ntiles);
+  const int n_m = c.B * c.m_tiles;
+
+  const int halo = (K / 2) * a.dil;
+  const int W = kTc2M + 2 * halo;
+  const bool gen = a.gen_w != nullptr;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + c.off_bar);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kBarCount);
+  uint32_t acc_stride = 32;
+  while (acc_stride < (uint32_t)a.N_tile) acc_stride <<= 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + kBarBFull + i, 1);
+      mbar_init(bars + kBarBEmpty + i, 1);
+      mbar_init(bars + kBarAccFull + i, 1);
+      mbar_init(bars + kBarAccEmpty + i, kTc3EpiThreads);
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(bars + kBarAFull + i, kTc3XformThreads);
+      mbar_init(bars + kBarAEmpty + i, 1);
+    }
+    mbar_init(bars + kBarWFull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(s_tmem, 2 * acc_stride);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int nvalid = min(a.N_tile, a.C_out - nt * a.N_tile);  // valid output channels of this N tile
+  const int n_sub = (nvalid + c.nsub - 1) / c.nsub;           // epilogue sub-tiles of this N tile
+  const int co_tile = nt * a.N_tile;
+
+  if (warp == 0) {
+    // =============================== WEIGHTS ===============================
+    if (lane == 0) {
+      const uint8_t* w_nt =
+          reinterpret_cast<const uint8_t*>(a.w + prob * L.d_w) + (size_t)nt * a.n_blk * c.b_bytes;
+      if (a.w_resident) {
+        const uint32_t total = c.b_bytes * a.n_blk;
+        mbar_expect_tx(bars + kBarWFull, total);
+        for (uint32_t o = 0; o < total; o += 32768u)
+          bulk_g2s(smem + c.off_w + o, w_nt + o, min(32768u, total - o), bars + kBarWFull);
+      } else {
+        uint32_t pbk = 0;
+        for (int m = first; m < n_m; m += step) {
+          for (int blk = 0; blk < a.n_blk; ++blk, ++pbk) {
+            const uint32_t slot = pbk & 1u, use = pbk >> 1;
+            if (use > 0) mbar_wait2(bars + kBarBEmpty + slot, (use + 1) & 1u);
+            mbar_expect_tx(bars + kBarBFull + slot, c.b_bytes);
+            const uint8_t* src = w_nt + (size_t)blk * c.b_bytes;
+            uint8_t* dst = smem + c.off_b + slot * c.b_bytes;
+            for (uint32_t o = 0; o < c.b_bytes; o += 32768u)
+              bulk_g2s(dst + o, src + o, min(32768u, c.b_bytes - o), bars + kBarBFull + slot);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA ISSUER ===============================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTc2M, a.N_tile);
+      const uint32_t Gb = (uint32_t)a.CIB >> 3;
+      const uint32_t strip = (uint32_t)W * 16u, a_plane = Gb * strip;
+      const uint32_t b_strip = (uint32_t)a.N_tile * 16u, b_half = (uint32_t)K * Gb * b_strip;
+      if (a.w_resident) mbar_wait2(bars + kBarWFull, 0);
+      uint32_t pa_pos = 0, pbk = 0;
+      int it = 0;
+      for (int m = first; m < n_m; m += step, ++it) {
+        const uint32_t acc = (uint32_t)it & 1u;
+        if (it >= 2) mbar_wait2(bars + kBarAccEmpty + acc, (((uint32_t)it >> 1) + 1) & 1u);
+        const uint32_t d_tmem = tmem + acc * acc_stride;
+        for (int blk = 0; blk < a.n_blk; ++blk) {
+          const uint32_t aslot = pa_pos % (uint32_t)c.a_slots, ause = pa_pos / (uint32_t)c.a_slots;
+          mbar_wait2(bars + kBarAFull + aslot, ause & 1u);
+          uint32_t sB_addr;
+          const uint32_t bslot = pbk & 1u;
+          if (a.w_resident) {
+            sB_addr = smem_u32(smem + c.off_w + (size_t)blk * c.b_bytes);
+          } else {
+            mbar_wait2(bars + kBarBFull + bslot, (pbk >> 1) & 1u);
+            sB_addr = smem_u32(smem + c.off_b + bslot * c.b_bytes);
+          }
+          tc_fence_after();
+          const uint32_t sA_addr = smem_u32(smem + c.off_a + aslot * c.a_bytes);
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            for (uint32_t kc = 0; kc < (uint32_t)a.CIB / 16u; ++kc) {
+              const uint32_t a_off = 2u * kc * strip + (uint32_t)(k * a.dil) * 16u;
+              const uint32_t b_off = ((uint32_t)k * Gb + 2u * kc) * b_strip;
+              const uint64_t a_hi = umma_desc(sA_addr + a_off, strip, 128);
+              const uint64_t a_lo = umma_desc(sA_addr + a_plane + a_off, strip, 128);
+              const uint64_t b_hi = umma_desc(sB_addr + b_off, b_strip, 128);
+              const uint64_t b_lo = umma_desc(sB_addr + b_half + b_off, b_strip, 128);
+              const uint32_t accum = (blk == 0 && k == 0 && kc == 0) ? 0u : 1u;
+              umma_bf16(d_tmem, a_lo, b_hi, idesc, accum);  // small terms first, then the dominant one
+              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+          }
+          umma_commit(bars + kBarAEmpty + aslot);
+          if (!a.w_resident) {
+            umma_commit(bars + kBarBEmpty + bslot);
+            ++pbk;
+          }
+          if (blk == a.n_blk - 1) umma_commit(bars + kBarAccFull + acc);
+          ++pa_pos;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // =============================== TRANSFORM ===============================
+    const int tt = tid - 64;
+    const float* in = a.in + prob * L.d_in;  // gen mode: 1-channel signal [B][T_in]
+    const float* gen_w = gen ? a.gen_w + prob * L.d_gen_w : nullptr;
+    const float* gen_b = gen ? a.gen_b + prob * L.d_gen_b : nullptr;
+    float* s_pa_base = reinterpret_cast<float*>(smem + c.off_pa);
+    const int cpad = (a.C_in + 7) / 8 * 8;
+    const int Gb = a.CIB >> 3;  // groups of 8 channels per (padded) ci block
+    const uint32_t strip = (uint32_t)W * 16u, plane = (uint32_t)Gb * strip;
+    const uint32_t gb_magic = 0xFFFFFFFFu / (uint32_t)Gb + 1u;    // exact quotients below 2^16
+    const uint32_t up_magic = 0xFFFFFFFFu / (uint32_t)a.up + 1u;
+    const int items = W * Gb;
+    constexpr int CH = kTc3ChunkItems, CHUNK = CH * kTc3XformThreads;
+    const int n_chunks = (items + CHUNK - 1) / CHUNK;
+
+    struct Cursor {
+      int m, blk, ch, it;
+    };
+    auto advance = [&](Cursor& q) {
+      if (++q.ch == n_chunks) {
+        q.ch = 0;
+        if (++q.blk == a.n_blk) {
+          q.blk = 0;
+          q.m += step;
+          ++q.it;
+        }
+      }
+    };
+    // issue the loads of one chunk (no use of the results)
+    auto load_chunk = [&](const Cursor& q, float4 (&d)[CH][2], uint32_t& live) {
+      live = 0;
+      if (q.m >= n_m) return;
+      const int b = q.m / c.m_tiles, t0 = (q.m - b * c.m_tiles) * kTc2M;
+      const int ci0 = q.blk * a.CIB;
+      if (q.blk == 0 && q.ch == 0 && a.pre_a) {  // InstanceNorm affine of this tile's utterance, one chunk early
+        float* s_pa = s_pa_base + (q.it & 1) * 2 * cpad;
+        for (int ch = tt; ch < cpad; ch += kTc3XformThreads) {
+          s_pa[ch] = ch < a.C_in ? __ldg(a.pre_a + (long long)b * a.C_in + ch) : 1.f;
+          s_pa[cpad + ch] = ch < a.C_in ? __ldg(a.pre_c + (long long)b * a.C_in + ch) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int idx = q.ch * CHUNK + j * kTc3XformThreads + tt;
+        if (idx < items) {
+          const int r = (int)__umulhi((uint32_t)idx, gb_magic), g = idx - r * Gb;
+          const int u = t0 - halo + r, ch = ci0 + g * 8;
+          if (u >= 0 && u < a.T_out && ch < a.C_in) {
+            live |= 1u << j;
+            if (gen) {
+              const float* x = in + (long long)b * a.T_in + u;
+              d[j][0].x = u > 0 ? __ldg(x - 1) : 0.f;
+              d[j][0].y = __ldg(x);
+              d[j][0].z = u + 1 < a.T_out ? __ldg(x + 1) : 0.f;
+            } else {
+              const int src = (a.up == 1 ? u : (int)__umulhi((uint32_t)u, up_magic)) * a.down;
+              const float4* p = reinterpret_cast<const float4*>(in + ((long long)b * a.T_in + src) * a.in_ld + ch);
+              d[j][0] = __ldg(p);
+              d[j][1] = __ldg(p + 1);
+            }
+          }
+        }
+      }
+    };
+    uint32_t pa_pos = 0;
+    auto convert_chunk = [&](const Cursor& q, const float4 (&d)[CH][2], uint32_t live) {
+      const uint32_t aslot = pa_pos % (uint32_t)c.a_slots, ause = pa_pos / (uint32_t)c.a_slots;
+      if (q.ch == 0) {
+        if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
+        if (q.blk == 0 && a.pre_a) named_bar_sync(1, kTc3XformThreads);  // s_pa of this tile is complete
+      }
+      uint8_t* sA = smem + c.off_a + aslot * c.a_bytes;
+      const float* s_pa = s_pa_base + (q.it & 1) * 2 * cpad;
+      const float* s_pc = s_pa + cpad;
+      const int ci0 = q.blk * a.CIB;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int idx = q.ch * CHUNK + j * kTc3XformThreads + tt;
+        if (idx < items) {
+          const int r = (int)__umulhi((uint32_t)idx, gb_magic), g = idx - r * Gb;
+          const int ch = ci0 + g * 8;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          if (live & (1u << j)) {
+            if (gen) {
+              const float x0 = fmaxf(d[j][0].x, d[j][0].x * a.slope), x1 = fmaxf(d[j][0].y, d[j][0].y * a.slope),
+                          x2 = fmaxf(d[j][0].z, d[j][0].z * a.slope);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float* gw = gen_w + ch + e;  // packed [tap][C_in]
+                float y = __ldg(gen_b + ch + e);
+                y = fmaf(__ldg(gw), x0, y);
+                y = fmaf(__ldg(gw + a.C_in), x1, y);
+                y = fmaf(__ldg(gw + 2 * a.C_in), x2, y);
+                v[e] = y;
+              }
+            } else {
+              v[0] = d[j][0].x; v[1] = d[j][0].y; v[2] = d[j][0].z; v[3] = d[j][0].w;
+              v[4] = d[j][1].x; v[5] = d[j][1].y; v[6] = d[j][1].z; v[7] = d[j][1].w;
+              if (a.pre_a) {
+                const float4* pa4 = reinterpret_cast<const float4*>(s_pa + ch);
+                const float4* pc4 = reinterpret_cast<const float4*>(s_pc + ch);
+                const float4 a0 = pa4[0], a1 = pa4[1], c0 = pc4[0], c1 = pc4[1];
+                v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
+                v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
+                v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
+                v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+              }
+            }
+            if (a.pre_lrelu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], v[e] * a.slope);  // slope in (0, 1)
+            }
+          }
+          split_store(sA + (uint32_t)g * strip + (uint32_t)r * 16u, plane, v);
+        }
+      }
+      if (q.ch == n_chunks - 1) {
+        fence_proxy_async();
+        mbar_arrive(bars + kBarAFull + aslot);
+        ++pa_pos;
+      }
+    };
+    // software pipeline over the chunk sequence: chunk k+1 is in flight while chunk k is converted
+    Cursor cur{first, 0, 0, 0};
+    float4 d0[CH][2], d1[CH][2];
+    uint32_t live0, live1;
+    load_chunk(cur, d0, live0);
+    while (cur.m < n_m) {
+      Cursor nxt = cur;
+      advance(nxt);
+      load_chunk(nxt, d1, live1);
+      convert_chunk(cur, d0, live0);
+      if (nxt.m >= n_m) break;
+      cur = nxt;
+      advance(nxt);
+      load_chunk(nxt, d0, live0);
+      convert_chunk(cur, d1, live1);
+      cur = nxt;
+    }
+  } else {
+    // =============================== EPILOGUE ===============================
+    const int ew = warp - 6;
+    const int q = warp & 3, h = ew >> 2;
+    const float* bias = a.bias + prob * L.d_bias;
+    const float* res = a.res ? a.res + prob * L.d_res : nullptr;
+    const float* gres_w = a.gres_w ? a.gres_w + prob * L.d_gres_w : nullptr;
+    const float* gres_b = a.gres_w ? a.gres_b + prob * L.d_gres_b : nullptr;
+    const float* gres_x = a.gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
+    float* raw = a.raw ? a.raw + prob * L.d_raw : nullptr;
+    float* out = a.out ? a.out + prob * L.d_out : nullptr;
+    const bool has_film = a.gamma != nullptr;
+    float* scr = reinterpret_cast<float*>(smem + c.off_scr) + ew * 32 * c.scr_pitch;
+
+    // operands of one (tile, sub-tile) unit for this thread: requested one unit ahead of their use
+    float4 o_res[4], o_ga[4], o_be[4];
+    float o_gx = 0.f;
+    auto load_ops = [&](int m, int sub) {
+      if (m >= n_m) return;
+      const int b = m / c.m_tiles, t0 = (m - b * c.m_tiles) * kTc2M;
+      const int t = t0 + q * 32 + lane;
+      if (t >= a.T_out) return;
+      const long long row = (long long)b * a.T_out + t;
+      const int nh = min(c.nsub, nvalid - sub * c.nsub) >> 1;
+      const int co = co_tile + sub * c.nsub + h * nh;
+      if (gres_w) o_gx = __ldg(gres_x + row);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (4 * j < nh) {
+          if (res) o_res[j] = __ldg(reinterpret_cast<const float4*>(res + row * a.res_ld + co) + j);
+          if (has_film) {
+            o_ga[j] = __ldg(reinterpret_cast<const float4*>(a.gamma + row * a.gb_ld + co) + j);
+            o_be[j] = __ldg(reinterpret_cast<const float4*>(a.beta + row * a.gb_ld + co) + j);
+          }
+        }
+      }
+    };
+    load_ops(first, 0);
+    int it = 0;
+    for (int m = first; m < n_m; m += step, ++it) {
+      const int b = m / c.m_tiles, t0 = (m - b * c.m_tiles) * kTc2M;
+      const uint32_t acc = (uint32_t)it & 1u;
+      const int t = t0 + q * 32 + lane;
+      const bool ok = t < a.T_out;
+      const long long row = (long long)b * a.T_out + t;
+      const int n_rows_seg = min(32, a.T_out - (t0 + q * 32));
+      const int seg = (t0 >> 5) + q;
+      mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      for (int sub = 0; sub < n_sub; ++sub) {
+        const int nh = min(c.nsub, nvalid - sub * c.nsub) >> 1;  // channels of this thread (multiple of 4, <= 16)
+        const int n4 = nh >> 2;
+        const int col = sub * c.nsub + h * nh;                  // first column inside the N tile
+        const int co = co_tile + col;
+        float v[16];
+        const uint32_t taddr = tmem + acc * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < n4) tmem_ld4_nowait(taddr + 4u * j, v + 4 * j);
+        tmem_ld_wait();
+        const float gx = o_gx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < n4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
+            float x[4] = {v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w};
+            if (res && ok) {
+              x[0] += o_res[j].x; x[1] += o_res[j].y; x[2] += o_res[j].z; x[3] += o_res[j].w;
+            }
+            if (gres_w) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(gres_w + co) + j);
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(gres_b + co) + j);
+              x[0] += fmaf(w4.x, gx, c4.x); x[1] += fmaf(w4.y, gx, c4.y);
+              x[2] += fmaf(w4.z, gx, c4.z); x[3] += fmaf(w4.w, gx, c4.w);
+            }
+            if (raw && ok) reinterpret_cast<float4*>(raw + row * a.raw_ld + co)[j] = make_float4(x[0], x[1], x[2], x[3]);
+            if (a.post_lrelu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], x[e] * a.slope);
+            }
+            if (has_film) {
+              if (ok) {
+                x[0] = fmaf(o_ga[j].x, x[0], o_be[j].x); x[1] = fmaf(o_ga[j].y, x[1], o_be[j].y);
+                x[2] = fmaf(o_ga[j].z, x[2], o_be[j].z); x[3] = fmaf(o_ga[j].w, x[3], o_be[j].w);
+              } else {
+                x[0] = x[1] = x[2] = x[3] = 0.f;
+              }
+            }
+            if (out && ok) reinterpret_cast<float4*>(out + row * a.out_ld + co)[j] = make_float4(x[0], x[1], x[2], x[3]);
+            v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
+          }
+        }
+        // request the next unit's operands now; they land while this thread waits for the next accumulator
+        if (sub + 1 < n_sub) load_ops(m, sub + 1);
+        else load_ops(m + step, 0);
+        if (a.stats && n_rows_seg > 0) {
+          // (mean, M2) of the stored values over this warp's <= 32 rows, per channel: transpose through the
+          // warp's smem scratch, then lane (half, ch) sums 16 rows about their first sample; the two halves
+          // are merged with Chan's formula.  in_finalize2_kernel merges the segments in double.
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < n4)
+              reinterpret_cast<float4*>(scr + lane * c.scr_pitch)[j] =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          const int hh = lane >> 4, ch = lane & 15;
+          const int cnt = max(0, min(16, n_rows_seg - 16 * hh));
+          float piv = 0.f, s1 = 0.f, s2 = 0.f;
+          if (ch < nh && cnt > 0) {
+            const float* col_p = scr + (16 * hh) * c.scr_pitch + ch;
+            piv = col_p[0];
+#pragma unroll 4
+            for (int i = 1; i < cnt; ++i) {
+              const float dd = col_p[i * c.scr_pitch] - piv;
+              s1 += dd;
+              s2 = fmaf(dd, dd, s2);
+            }
+          }
+          const float n1 = (float)cnt;
+          float mean = cnt > 0 ? piv + s1 / n1 : 0.f;
+          float m2 = cnt > 0 ? fmaxf(s2 - s1 * s1 / n1, 0.f) : 0.f;
+          const float mean_o = __shfl_xor_sync(0xffffffffu, mean, 16);
+          const float m2_o = __shfl_xor_sync(0xffffffffu, m2, 16);
+          const float n_o = __shfl_xor_sync(0xffffffffu, n1, 16);
+          if (hh == 0 && ch < nh) {
+            const float nn = n1 + n_o;
+            const float dd = mean_o - mean;
+            mean += dd * n_o / nn;
+            m2 += m2_o + dd * dd * n1 * n_o / nn;
+            a.stats[((long long)b * a.n_seg + seg) * a.C_out + co + ch] = make_float2(mean, m2);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bars + kBarAccEmpty + acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem, 2 * acc_stride);
+  }
+}
+
+// (B, C, T) -> [B][T][C]: the caller's PPG tensor into the channels-last form the bulk-copy producer reads.
+__global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict__ x, int C, int T, float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + tx;
+    tile[i][tx] = (c < C && t < T) ? x[((long long)b * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + tx;
+    if (t < T && c < C) y[((long long)b * T + t) * C + c] = tile[tx][i];
+  }
+}
+
+}  // namespace fsvc

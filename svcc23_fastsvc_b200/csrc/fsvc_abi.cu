@@ -12,6 +12,8 @@
 #include "conv_f32.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
+#include "conv_tc3.cuh"
+#include "level_fused.cuh"
 
 namespace fsvc {
 
@@ -38,6 +40,7 @@ struct ConvW {  // packed [C_in][K][C_out] + bias[C_out], device
   TcW tc;   // tensor-core copy of the same weights (tc.w == nullptr: conv not eligible)
   TcW tc2;  // copy tiled for the persistent channels-last kernel (conv_tc2.cuh)
   int tc2_resident = 0;
+  int ctx_dil = 1, ctx_up = 1;  // how the generator uses this conv (dilation, upsampling factor of its input)
 };
 
 // Tensor-core tiling of a conv: N tiles of <= 128 output channels (multiple of 16), input-channel
@@ -56,35 +59,60 @@ static bool tc_plan(int C_in, int C_out, int K, TcW* t) {
   return true;
 }
 
-// Tiling of a conv for conv_tc2_kernel: ci blocks of <= 64 channels, N tiles of <= 128 output channels;
-// weights stay resident in shared memory when they fit next to the 2-deep A ring at the widest
-// dilation (27).  Independent of the batch size, so results never depend on it.
+// Tiling of a conv for the warp-specialised kernel (conv_tc3.cuh): N tiles of <= 128 output channels,
+// ci blocks of <= 64 input channels, weights resident in shared memory when they fit next to the rings.
+// It depends only on the conv
+// (never on the batch size), so results are independent of how utterances are batched.
 static bool tc2_plan(int C_in, int C_out, int K, ConvW* cw) {
   TcW* t = &cw->tc2;
-  if (C_out % 8 != 0 || C_in < 8) return false;
+  if (C_out % 8 != 0 || C_in % 8 != 0 || C_in < 8) return false;
   const int c16 = (C_in + 15) / 16 * 16;
-  t->n_blk = (c16 + 63) / 64;
-  t->CIB = ((c16 + t->n_blk - 1) / t->n_blk + 15) / 16 * 16;
   const int n16 = (C_out + 15) / 16 * 16;
   t->n_ntiles = (n16 + 127) / 128;
   t->N_tile = ((n16 + t->n_ntiles - 1) / t->n_ntiles + 15) / 16 * 16;
   t->N_alloc = 32;
   while (t->N_alloc < t->N_tile) t->N_alloc *= 2;
   t->K = K;
-  const size_t budget = (size_t)200 * 1024;
-  const int W_max = kTc2M + 2 * 27;
-  const size_t wbytes = (size_t)2 * K * t->CIB * t->n_blk * t->N_tile * 2;
-  const size_t abytes = (size_t)2 * (t->CIB / 8) * W_max * 16;
-  cw->tc2_resident = (wbytes + 2 * abytes + 4096 <= budget) ? 1 : 0;
-  if (!cw->tc2_resident) {
-    // streamed weights: the (N tile, ci block) chunk rides in the ring next to the A block
-    for (int cib = 64; cib >= 16; cib -= 16) {
-      t->CIB = cib;
-      t->n_blk = (c16 + cib - 1) / cib;
-      const size_t b_blk = (size_t)2 * K * cib * t->N_tile * 2, a_blk = (size_t)2 * (cib / 8) * W_max * 16;
-      if (2 * (b_blk + a_blk) + 4096 <= budget) break;
+  Tc2Args a;
+  memset(&a, 0, sizeof(a));
+  a.C_in = C_in;
+  a.C_out = C_out;
+  a.N_tile = t->N_tile;
+  a.n_ntiles = t->n_ntiles;
+  a.dil = cw->ctx_dil;
+  a.up = cw->ctx_up;
+  a.down = 1;
+  a.res = (const float*)1;  // plan for the widest epilogue (residual + FiLM operands)
+  a.gamma = (const float*)1;
+  // largest ci block whose A ring is at least double-buffered (resident weights first); else anything that fits
+  int best_cib = 0, best_res = 0, fb_cib = 0, fb_res = 0;
+  const int nat_blk = (c16 + 63) / 64;
+  const int nat_cib = ((c16 + nat_blk - 1) / nat_blk + 15) / 16 * 16;
+  for (int cib = nat_cib; cib >= 16 && !best_cib; cib -= 16) {
+    for (int resident = 1; resident >= 0 && !best_cib; --resident) {
+      a.CIB = cib;
+      a.n_blk = (c16 + cib - 1) / cib;
+      a.w_resident = resident;
+      Tc3Cfg cfg;
+      if (!tc3_plan_smem(a, K, &cfg)) continue;
+      if (!fb_cib) {
+        fb_cib = cib;
+        fb_res = resident;
+      }
+      if (cfg.a_slots >= 2) {
+        best_cib = cib;
+        best_res = resident;
+      }
     }
   }
+  if (!best_cib) {
+    best_cib = fb_cib;
+    best_res = fb_res;
+  }
+  if (!best_cib) return false;
+  t->CIB = best_cib;
+  t->n_blk = (c16 + best_cib - 1) / best_cib;
+  cw->tc2_resident = best_res;
   return true;
 }
 
@@ -418,6 +446,9 @@ static int tc_setup_kernels() {
   FSVC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(level0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return FSVC_OK;
 }
 
@@ -552,6 +583,8 @@ struct WS2 {
       *t2[FSVC_MAX_STAGES], *xs[FSVC_MAX_STAGES];
   float2* stats;                 // [B][n_seg][C]
   float *pa, *pc;                // [B][C]
+  float* xin;                    // [B][frames][in_channels] channels-last copy of the PPG input
+  float* ydec[2];                // [B][T/s][C0] level-0 output decimated for level 1 (fused level kernel)
 };
 
 static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, size_t cap, WS2* ws) {
@@ -592,6 +625,8 @@ static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, si
   ws->stats = ar.get<float2>(max_stat);
   ws->pa = ar.get<float>(max_bc);
   ws->pc = ar.get<float>(max_bc);
+  ws->xin = ar.get<float>((size_t)B * frames * h->cfg.in_channels);
+  for (int br = 0; br < 2; ++br) ws->ydec[br] = ar.get<float>((size_t)B * T * h->lvl_c[0]);
   return ar.off;
 }
 
@@ -622,34 +657,51 @@ static Tc2Args tc2_args(const Ctx& c, const ConvW& w, const float* in, int in_ld
   return a;
 }
 
-// Launch 1 or 2 problems of identical tiling (same conv shape) as one persistent grid.
+// Launch 1 or 2 problems of identical shape and flags (the two conditioning branches) as one persistent grid
+// of the warp-specialised kernel; problem 1 is expressed as pointer deltas against problem 0.
 static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, int n_prob, const char* name) {
-  Tc2Batch pb;
-  memset(&pb, 0, sizeof(pb));
-  for (int i = 0; i < n_prob; ++i) pb.p[i] = p[i];
-  pb.n_prob = n_prob;
-  pb.B = c.B;
-  pb.m_tiles = (p[0].T_out + kTc2M - 1) / kTc2M;
-  const int W = kTc2M + 2 * (K / 2) * p[0].dil;
-  const Tc2Smem L = tc2_smem_layout(K, p[0].CIB, p[0].n_blk, p[0].N_tile, p[0].w_resident, W, p[0].C_in);
-  int acc_stride = 32;
-  while (acc_stride < p[0].N_tile) acc_stride *= 2;
-  int per_sm = (int)((size_t)(227 * 1024) / ((size_t)L.total + 1024));
-  per_sm = per_sm < 1 ? 1 : per_sm;
-  if (per_sm > 2) per_sm = 2;  // __launch_bounds__(256, 2)
-  if (per_sm * 2 * acc_stride > 512) per_sm = 512 / (2 * acc_stride);
-  const int groups = n_prob * p[0].n_ntiles;
-  const int items = c.B * pb.m_tiles;
-  int per_group = (h->num_sms * per_sm) / groups;
-  per_group = per_group < 1 ? 1 : per_group;
-  per_group = per_group > items ? items : per_group;
-  const dim3 grid(per_group * groups);
-  if (L.total > 227u * 1024u) {
+  Tc3Launch L;
+  memset(&L, 0, sizeof(L));
+  L.a = p[0];
+  if (n_prob == 2) {
+    const Tc2Args &x = p[0], &y = p[1];
+    L.d_in = y.in - x.in;
+    L.d_w = y.w - x.w;
+    L.d_bias = y.bias - x.bias;
+    L.d_gen_w = x.gen_w ? y.gen_w - x.gen_w : 0;
+    L.d_gen_b = x.gen_w ? y.gen_b - x.gen_b : 0;
+    L.d_res = x.res ? y.res - x.res : 0;
+    L.d_gres_w = x.gres_w ? y.gres_w - x.gres_w : 0;
+    L.d_gres_b = x.gres_w ? y.gres_b - x.gres_b : 0;
+    L.d_gres_x = x.gres_w ? y.gres_x - x.gres_x : 0;
+    L.d_raw = x.raw ? y.raw - x.raw : 0;
+    L.d_out = x.out ? y.out - x.out : 0;
+    // everything that is not a per-problem pointer must agree
+    if (x.pre_lrelu != y.pre_lrelu || x.post_lrelu != y.post_lrelu || x.gamma != y.gamma || x.stats != y.stats ||
+        x.pre_a != y.pre_a || x.up != y.up || x.down != y.down || x.dil != y.dil || x.C_in != y.C_in ||
+        x.C_out != y.C_out || x.T_out != y.T_out || x.T_in != y.T_in || x.in_ld != y.in_ld ||
+        x.out_ld != y.out_ld || x.res_ld != y.res_ld || (x.res == nullptr) != (y.res == nullptr) ||
+        (x.gen_w == nullptr) != (y.gen_w == nullptr) || (x.gres_w == nullptr) != (y.gres_w == nullptr)) {
+      c.err = 2;
+      return;
+    }
+  }
+  Tc3Cfg& cfg = L.c;
+  cfg.n_prob = n_prob;
+  cfg.B = c.B;
+  cfg.m_tiles = (p[0].T_out + kTc2M - 1) / kTc2M;
+  if (!tc3_plan_smem(p[0], K, &cfg)) {
     c.err = 1;
     return;
   }
-  if (K == 3) conv_tc2_kernel<3><<<grid, kTc2Threads, L.total, c.stream>>>(pb);
-  else conv_tc2_kernel<1><<<grid, kTc2Threads, L.total, c.stream>>>(pb);
+  const int groups = n_prob * p[0].n_ntiles;
+  const int items = c.B * cfg.m_tiles;
+  int per_group = h->num_sms / groups;
+  per_group = per_group < 1 ? 1 : per_group;
+  per_group = per_group > items ? items : per_group;
+  const dim3 grid(per_group * groups);
+  if (K == 3) conv_tc3_kernel<3><<<grid, kTc3Threads, cfg.total, c.stream>>>(L);
+  else conv_tc3_kernel<1><<<grid, kTc3Threads, cfg.total, c.stream>>>(L);
   double flops = 0, elems = 0;
   for (int i = 0; i < n_prob; ++i) {
     const Tc2Args& a = p[i];
@@ -660,6 +712,23 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     elems += (double)a.C_in * a.C_out * K;
   }
   c.launched(name, flops, 4.0 * elems);
+}
+
+// The full-rate conditioning level runs as ONE fused kernel (level_fused.cuh) when its channel count is small
+// enough for every weight of the level to stay in shared memory next to three activation buffers.
+static bool level0_fusable(const fsvc_handle* h, LevelFusedSmem* Lout) {
+  const LevelW& lw = h->level[0];
+  const int C = h->lvl_c[0];
+  if (lw.c1[0].C_in != 1 || C % 8 != 0 || C > 32) return false;
+  for (int br = 0; br < 2; ++br)
+    for (const ConvW* cw : {&lw.c2[br], &lw.c4[br], &lw.film[br]})
+      if (!cw->tc2.w || cw->tc2.n_blk != 1 || cw->tc2.n_ntiles != 1 || cw->tc2.N_tile > 64) return false;
+  const TcW& fo = lw.film_out.tc2;
+  if (!fo.w || fo.n_blk != 1 || fo.n_ntiles != 1 || fo.CIB != 2 * C || fo.N_tile > 64) return false;
+  const LevelFusedSmem L = level_fused_smem(C, lw.c2[0].tc2.CIB / 8, lw.c2[0].tc2.N_tile, fo.N_tile);
+  if (L.total > 227u * 1024u) return false;
+  if (Lout) *Lout = L;
+  return true;
 }
 
 static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk,
@@ -695,12 +764,54 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
 
   // ---- conditioning chains, both branches per launch (fastsvc.py:180-193, 220-232) ----
   int T_prev = T, T_l = T;
+  bool fused_l0 = false;
   for (int l = 0; l < n; ++l) {
     T_l = T_prev / h->dscale[l];
     const LevelW& lw = h->level[l];
     const int C = h->lvl_c[l];
     c.label = lvl_label[l];
     Tc2Args p[2];
+    LevelFusedSmem LF;
+    if (l == 0 && level0_fusable(h, &LF)) {
+      LevelFusedArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      const int dec = n > 1 ? h->dscale[1] : 1;
+      for (int br = 0; br < 2; ++br) {
+        fa.sig[br] = br == 0 ? lft : sine;
+        fa.c1_w[br] = lw.c1[br].w;
+        fa.c1_b[br] = lw.c1[br].b;
+        fa.r1_w[br] = lw.r1[br].w;
+        fa.r1_b[br] = lw.r1[br].b;
+        fa.w_c2[br] = lw.c2[br].tc2.w;
+        fa.w_c4[br] = lw.c4[br].tc2.w;
+        fa.w_film[br] = lw.film[br].tc2.w;
+        fa.b_c2[br] = lw.c2[br].b;
+        fa.b_c4[br] = lw.c4[br].b;
+        fa.b_film[br] = lw.film[br].b;
+        fa.y_dec[br] = (n > 1 && T_l % dec == 0) ? ws.ydec[br] : nullptr;
+      }
+      fa.w_out = lw.film_out.tc2.w;
+      fa.b_out = lw.film_out.b;
+      fa.gb = ws.GB[0];
+      fa.C = C;
+      fa.T = T_l;
+      fa.B = B;
+      fa.dec = dec;
+      fa.n_tiles = (T_l + kLfValid - 1) / kLfValid;
+      fa.Gp = lw.c2[0].tc2.CIB / 8;
+      fa.N1 = lw.c2[0].tc2.N_tile;
+      fa.N2 = lw.film_out.tc2.N_tile;
+      fa.slope = c.slope;
+      const int items = B * fa.n_tiles;
+      const int grid = items < h->num_sms ? items : h->num_sms;
+      level0_fused_kernel<<<grid, kLfThreads, LF.total, stream>>>(fa);
+      const double BT = (double)B * T_l;
+      c.launched("fused_level", 2.0 * BT * C * (2.0 * (3 + 1 + 9.0 * C) + 2.0 * 9 * C + 12.0 * C),
+                 4.0 * (2 * BT + 2 * BT * C / dec + 2 * BT * C));
+      fused_l0 = true;
+      T_prev = T_l;
+      continue;
+    }
     if (lw.c1[0].C_in == 1) {
       // 1-channel input: the first conv (and the 1x1 residual) are generated inside the consumers
       for (int br = 0; br < 2; ++br) {
@@ -723,14 +834,18 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
       launch_tc2(c, h, 3, p, 2, "down_d4+r");
     } else {
       const int Cp = h->lvl_c[l - 1];
+      // the fused level-0 kernel hands over its output already decimated
+      const bool dec_in = l == 1 && fused_l0;
       for (int br = 0; br < 2; ++br) {
-        p[br] = tc2_args(c, lw.r1[br], ws.y[br][l - 1], Cp, T_prev, T_l, 1, ws.tr[br], C);
-        p[br].down = h->dscale[l];
+        p[br] = tc2_args(c, lw.r1[br], dec_in ? ws.ydec[br] : ws.y[br][l - 1], Cp, dec_in ? T_l : T_prev, T_l, 1,
+                         ws.tr[br], C);
+        p[br].down = dec_in ? 1 : h->dscale[l];
       }
       launch_tc2(c, h, 1, p, 2, "down_r1x1");
       for (int br = 0; br < 2; ++br) {
-        p[br] = tc2_args(c, lw.c1[br], ws.y[br][l - 1], Cp, T_prev, T_l, 1, ws.ta[br], C);
-        p[br].down = h->dscale[l];
+        p[br] = tc2_args(c, lw.c1[br], dec_in ? ws.ydec[br] : ws.y[br][l - 1], Cp, dec_in ? T_l : T_prev, T_l, 1,
+                         ws.ta[br], C);
+        p[br].down = dec_in ? 1 : h->dscale[l];
         p[br].pre_lrelu = 1;
       }
       launch_tc2(c, h, 3, p, 2, "down_d1");
@@ -758,8 +873,14 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
   }
 
   // ---- upsampling stages (fastsvc.py:80-140) ----
-  const float* x = ppg;
-  int x_ld = 0, T_in = frames;
+  {  // the caller's (B, C, T') PPG tensor -> channels-last
+    const int Cin = h->cfg.in_channels;
+    nct_to_ntc_kernel<<<dim3((frames + 31) / 32, (Cin + 31) / 32, B), 256, 0, stream>>>(ppg, Cin, frames, ws.xin);
+    c.label = "";
+    c.launched("ppg_to_ntc", 0.0, 8.0 * B * Cin * frames);
+  }
+  const float* x = ws.xin;
+  int x_ld = h->cfg.in_channels, T_in = frames;
   for (int i = 0; i < n; ++i) {
     const StageW& w = h->stage[i];
     const int C = h->cfg.mid_channels[i], r = h->cfg.upsampling_scales[i];
@@ -792,17 +913,17 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
     Tc2Args p[2];
     // h0 = conv_first(x)                                                     fastsvc.py:93
     p[0] = tc2_args(c, w.first, x, x_ld, T_in, T_in, 1, ws.h0[i], C);
-    p[0].in_nct = i == 0 ? 1 : 0;
     launch_tc2(c, h, 3, p, 1, "conv_first");
     // xr = Conv3(repeat_r(h0)) ; t1 = gamma*lrelu(Conv3(repeat_r(lrelu(h0)))) + beta   :94, :97-98
     p[0] = tc2_args(c, w.res, ws.h0[i], C, T_in, T_s, 1, ws.xr[i], C);
     p[0].up = r;
-    p[1] = tc2_args(c, w.up, ws.h0[i], C, T_in, T_s, 1, ws.t1[i], C);
-    p[1].up = r;
-    p[1].pre_lrelu = 1;
-    p[1].post_lrelu = 1;
-    film(p[1]);
-    launch_tc2(c, h, 3, p, 2, "residual+up_film");
+    launch_tc2(c, h, 3, p, 1, "residual");
+    p[0] = tc2_args(c, w.up, ws.h0[i], C, T_in, T_s, 1, ws.t1[i], C);
+    p[0].up = r;
+    p[0].pre_lrelu = 1;
+    p[0].post_lrelu = 1;
+    film(p[0]);
+    launch_tc2(c, h, 3, p, 1, "up_film");
     finalize();
     // x_ = Conv3_d3(lrelu(IN(t1)+e)) + xr ; t2 = gamma*x_ + beta            :99-105
     p[0] = tc2_args(c, w.d3, ws.t1[i], C, T_s, T_s, 3, ws.t2[i], C);
@@ -840,7 +961,7 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
     c.launched("conv_last", 2.0 * BT * C * h->cfg.out_channels, 4.0 * BT * (C + h->cfg.out_channels));
   }
   h->launches = c.launches;
-  if (c.err) return fail(FSVC_E_INVALID, "internal: a conv tile does not fit in shared memory");
+  if (c.err) return fail(FSVC_E_INVALID, "internal: conv launch plan failed (code %d)", c.err);
   FSVC_CUDA(cudaGetLastError());
   return FSVC_OK;
 }
@@ -920,6 +1041,10 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
     add_conv(s.d9, p + ".conv_block2.1", C, C, 3);
     add_conv(s.d27, p + ".conv_block3.1", C, C, 3);
     add_conv(s.res, p + ".residual_block.1", C, C, 3);
+    s.up.ctx_up = s.res.ctx_up = cfg->upsampling_scales[i];
+    s.d3.ctx_dil = 3;
+    s.d9.ctx_dil = 9;
+    s.d27.ctx_dil = 27;
     if (cfg->use_spk_emb) {
       fixp.push_back({&s.emb_w, reserve((size_t)C * cfg->spk_emb_size)});
       fixp.push_back({&s.emb_b, reserve(C)});
@@ -938,6 +1063,8 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
       add_conv(h->level[l].c1[br], p + ".downsample_block.2", C, ci, 3);
       add_conv(h->level[l].c2[br], p + ".downsample_block.4", C, C, 3);
       add_conv(h->level[l].c4[br], p + ".downsample_block.6", C, C, 3);
+      h->level[l].c2[br].ctx_dil = 2;
+      h->level[l].c4[br].ctx_dil = 4;
       ci = C;
     }
   }
