@@ -77,17 +77,19 @@ struct Tc2Batch {  // up to 2 independent problems of identical tiling in one la
 constexpr int kTc2Threads = 256;
 constexpr int kTc2M = 128;
 
+// Wait for the phase with the given parity.  The suspend-time hint lets the hardware park the thread until
+// the phase completes instead of spinning (spinning waiters steal issue slots from the MMA-issuing warp).
 __device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred P1;\n"
       "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE_%=;\n"
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {

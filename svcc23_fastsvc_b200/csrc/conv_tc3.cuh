@@ -7,10 +7,10 @@
 //                          shared memory, else one (N tile, ci block) chunk per MMA block through a 2-slot ring
 //   warp 1      MMA        one thread issues tcgen05.mma (bf16 3-term split, fp32 accumulation in TMEM,
 //                          two accumulators so tile i+1 is computed while tile i is drained)
-//   warps 2-5   TRANSFORM  128-bit loads of the A window, issued one 512-item chunk AHEAD of their use
+//   warps 2-7   TRANSFORM  128-bit loads of the A window, issued one 768-item chunk AHEAD of their use
 //                          (register double buffer) -> InstanceNorm affine -> LeakyReLU -> zero padding
 //                          -> bf16 hi|lo in the UMMA K-major canonical layout (taps = descriptor row shifts)
-//   warps 6-13  EPILOGUE   TMEM -> registers (+bias, residual, FiLM affine) -> 128-bit row stores; the
+//   warps 8-15  EPILOGUE   TMEM -> registers (+bias, residual, FiLM affine) -> 128-bit row stores; the
 //                          residual / gamma / beta rows of the NEXT sub-tile are requested before the
 //                          current one is waited for; InstanceNorm partial statistics through a per-warp
 //                          shared-memory transpose
@@ -23,9 +23,10 @@
 
 namespace fsvc {
 
-constexpr int kTc3Threads = 448;
-constexpr int kTc3XformThreads = 128;  // warps 2..5
-constexpr int kTc3EpiThreads = 256;    // warps 6..13
+constexpr int kTc3XformWarps = 6;
+constexpr int kTc3XformThreads = 32 * kTc3XformWarps;  // warps 2..9
+constexpr int kTc3EpiThreads = 256;                    // the 8 warps after them
+constexpr int kTc3Threads = 64 + kTc3XformThreads + kTc3EpiThreads;
 constexpr int kTc3ChunkItems = 4;      // 16-byte-chunk items per transform thread and prefetch chunk
 
 struct Tc3Cfg {
@@ -79,7 +80,7 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c) {
   c->scr_pitch = nsub / 2 <= 12 ? 12 : 20;
   const uint32_t w_bytes = a.w_resident ? c->b_bytes * a.n_blk : 0u;
   const uint32_t scr_bytes = 8u * 32u * c->scr_pitch * 4u;
-  const uint32_t pa_bytes = 2u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;
+  const uint32_t pa_bytes = 3u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;  // triple-buffered per-utterance affine
   for (int slots = 3; slots >= 1; --slots) {
     c->a_slots = slots;
     uint32_t off = 0;
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + kTc3XformWarps) {
     // =============================== TRANSFORM ===============================
     const int tt = tid - 64;
     const float* in = a.in + prob * L.d_in;  // gen mode: 1-channel signal [B][T_in]
@@ -261,8 +262,10 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
       if (q.m >= n_m) return;
       const int b = q.m / c.m_tiles, t0 = (q.m - b * c.m_tiles) * kTc2M;
       const int ci0 = q.blk * a.CIB;
-      if (q.blk == 0 && q.ch == 0 && a.pre_a) {  // InstanceNorm affine of this tile's utterance, one chunk early
-        float* s_pa = s_pa_base + (q.it & 1) * 2 * cpad;
+      // InstanceNorm affine of this tile's utterance, written one chunk early.  Three buffers: the write for
+      // tile i+3 follows the named barrier of tile i+1, which every thread reaches only after converting tile i.
+      if (q.blk == 0 && q.ch == 0 && a.pre_a) {
+        float* s_pa = s_pa_base + (q.it % 3) * 2 * cpad;
         for (int ch = tt; ch < cpad; ch += kTc3XformThreads) {
           s_pa[ch] = ch < a.C_in ? __ldg(a.pre_a + (long long)b * a.C_in + ch) : 1.f;
           s_pa[cpad + ch] = ch < a.C_in ? __ldg(a.pre_c + (long long)b * a.C_in + ch) : 0.f;
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         if (q.blk == 0 && a.pre_a) named_bar_sync(1, kTc3XformThreads);  // s_pa of this tile is complete
       }
       uint8_t* sA = smem + c.off_a + aslot * c.a_bytes;
-      const float* s_pa = s_pa_base + (q.it & 1) * 2 * cpad;
+      const float* s_pa = s_pa_base + (q.it % 3) * 2 * cpad;
       const float* s_pc = s_pa + cpad;
       const int ci0 = q.blk * a.CIB;
 #pragma unroll
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
     }
   } else {
     // =============================== EPILOGUE ===============================
-    const int ew = warp - 6;
+    const int ew = warp - (2 + kTc3XformWarps);
     const int q = warp & 3, h = ew >> 2;
     const float* bias = a.bias + prob * L.d_bias;
     const float* res = a.res ? a.res + prob * L.d_res : nullptr;

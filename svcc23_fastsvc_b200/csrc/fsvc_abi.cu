@@ -41,6 +41,8 @@ struct ConvW {  // packed [C_in][K][C_out] + bias[C_out], device
   TcW tc2;  // copy tiled for the persistent channels-last kernel (conv_tc2.cuh)
   int tc2_resident = 0;
   int ctx_dil = 1, ctx_up = 1;  // how the generator uses this conv (dilation, upsampling factor of its input)
+  const __nv_bfloat16* wnc = nullptr;  // [tap][group][hi|lo rows][8] copy for the fused level kernel
+  int nc_G = 0, nc_N = 0;
 };
 
 // Tensor-core tiling of a conv: N tiles of <= 128 output channels (multiple of 16), input-channel
@@ -147,6 +149,7 @@ struct fsvc_handle {
   __nv_bfloat16* tc_store = nullptr;  // tensor-core (bf16 hi/lo) copies of the conv weights
   size_t tc_elems = 0;
   bool tc2_ok = false;                // every conv of the forward can run on conv_tc2_kernel
+  bool l0_fused = false;              // level 0 runs as the fused kernel (level_fused.cuh)
   int num_sms = 148;
   std::vector<ConvW*> convs;          // every conv of the generator (for the tensor-core repack)
   StageW stage[FSVC_MAX_STAGES];
@@ -714,23 +717,6 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   c.launched(name, flops, 4.0 * elems);
 }
 
-// The full-rate conditioning level runs as ONE fused kernel (level_fused.cuh) when its channel count is small
-// enough for every weight of the level to stay in shared memory next to three activation buffers.
-static bool level0_fusable(const fsvc_handle* h, LevelFusedSmem* Lout) {
-  const LevelW& lw = h->level[0];
-  const int C = h->lvl_c[0];
-  if (lw.c1[0].C_in != 1 || C % 8 != 0 || C > 32) return false;
-  for (int br = 0; br < 2; ++br)
-    for (const ConvW* cw : {&lw.c2[br], &lw.c4[br], &lw.film[br]})
-      if (!cw->tc2.w || cw->tc2.n_blk != 1 || cw->tc2.n_ntiles != 1 || cw->tc2.N_tile > 64) return false;
-  const TcW& fo = lw.film_out.tc2;
-  if (!fo.w || fo.n_blk != 1 || fo.n_ntiles != 1 || fo.CIB != 2 * C || fo.N_tile > 64) return false;
-  const LevelFusedSmem L = level_fused_smem(C, lw.c2[0].tc2.CIB / 8, lw.c2[0].tc2.N_tile, fo.N_tile);
-  if (L.total > 227u * 1024u) return false;
-  if (Lout) *Lout = L;
-  return true;
-}
-
 static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk,
                        float* out, int B, int frames, void* workspace, size_t ws_bytes, cudaStream_t stream,
                        Profiler* prof = nullptr) {
@@ -771,8 +757,9 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
     const int C = h->lvl_c[l];
     c.label = lvl_label[l];
     Tc2Args p[2];
-    LevelFusedSmem LF;
-    if (l == 0 && level0_fusable(h, &LF)) {
+    if (l == 0 && h->l0_fused) {
+      const LevelFusedSmem LF =
+          level_fused_smem(C, lw.c2[0].nc_G, lw.c2[0].nc_N, lw.film_out.nc_N);
       LevelFusedArgs fa;
       memset(&fa, 0, sizeof(fa));
       const int dec = n > 1 ? h->dscale[1] : 1;
@@ -782,15 +769,15 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
         fa.c1_b[br] = lw.c1[br].b;
         fa.r1_w[br] = lw.r1[br].w;
         fa.r1_b[br] = lw.r1[br].b;
-        fa.w_c2[br] = lw.c2[br].tc2.w;
-        fa.w_c4[br] = lw.c4[br].tc2.w;
-        fa.w_film[br] = lw.film[br].tc2.w;
+        fa.w_c2[br] = lw.c2[br].wnc;
+        fa.w_c4[br] = lw.c4[br].wnc;
+        fa.w_film[br] = lw.film[br].wnc;
         fa.b_c2[br] = lw.c2[br].b;
         fa.b_c4[br] = lw.c4[br].b;
         fa.b_film[br] = lw.film[br].b;
         fa.y_dec[br] = (n > 1 && T_l % dec == 0) ? ws.ydec[br] : nullptr;
       }
-      fa.w_out = lw.film_out.tc2.w;
+      fa.w_out = lw.film_out.wnc;
       fa.b_out = lw.film_out.b;
       fa.gb = ws.GB[0];
       fa.C = C;
@@ -798,9 +785,9 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
       fa.B = B;
       fa.dec = dec;
       fa.n_tiles = (T_l + kLfValid - 1) / kLfValid;
-      fa.Gp = lw.c2[0].tc2.CIB / 8;
-      fa.N1 = lw.c2[0].tc2.N_tile;
-      fa.N2 = lw.film_out.tc2.N_tile;
+      fa.Gp = lw.c2[0].nc_G;
+      fa.N1 = lw.c2[0].nc_N;
+      fa.N2 = lw.film_out.nc_N;
       fa.slope = c.slope;
       const int items = B * fa.n_tiles;
       const int grid = items < h->num_sms ? items : h->num_sms;
@@ -1113,6 +1100,28 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
   }
   for (int i = 0; i < n; ++i)
     if (cfg->mid_channels[i] % 8 != 0) h->tc2_ok = false;
+  {  // fused level-0 kernel: every weight of the level in shared memory next to four activation buffers
+    LevelW& lw = h->level[0];
+    const int C = h->lvl_c[0];
+    if (h->tc2_ok && C % 8 == 0 && C <= 32) {
+      const int Gp = (C / 8 + 1) / 2 * 2, N1 = (C + 15) / 16 * 16, N2 = (2 * C + 15) / 16 * 16;
+      if (level_fused_smem(C, Gp, N1, N2).total <= 227u * 1024u) {
+        h->l0_fused = true;
+        auto want = [&](ConvW& cw, int G, int N) {
+          cw.nc_G = G;
+          cw.nc_N = N;
+          cw.wnc = (const __nv_bfloat16*)tc_off;
+          tc_off += ((size_t)cw.K * G * 2 * N * 8 + 127) & ~(size_t)127;
+        };
+        for (int br = 0; br < 2; ++br) {
+          want(lw.c2[br], Gp, N1);
+          want(lw.c4[br], Gp, N1);
+          want(lw.film[br], Gp, N1);
+        }
+        want(lw.film_out, 2 * C / 8, N2);
+      }
+    }
+  }
   {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, h->device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
@@ -1127,6 +1136,7 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
   for (ConvW* cw : h->convs) {
     if (cw->tc.n_ntiles) cw->tc.w = h->tc_store + (size_t)cw->tc.w;
     if (cw->tc2.n_ntiles) cw->tc2.w = h->tc_store + (size_t)cw->tc2.w;
+    if (cw->nc_G) cw->wnc = h->tc_store + (size_t)cw->wnc;
   }
   if (int rc = tc_setup_kernels()) {
     cudaFree(h->store);
@@ -1223,6 +1233,11 @@ int fsvc_set_weights(fsvc_handle* h, const float* const* p, int n, void* stream_
   {
     if (cw->tc.w) pack_tc(s, *cw, cw->tc);
     if (cw->tc2.w) pack_tc(s, *cw, cw->tc2);
+    if (cw->nc_G) {
+      const size_t total = (size_t)cw->K * cw->nc_G * cw->nc_N * 8;
+      pack_tc_nc_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+          cw->w, cw->C_in, cw->C_out, cw->K, cw->nc_G, cw->nc_N, (__nv_bfloat16*)cw->wnc);
+    }
   }
   FSVC_CUDA(cudaGetLastError());
   h->weights_set = true;

@@ -19,6 +19,15 @@
 // Work item = (utterance, 238 output steps): 2 MMA M-tiles (256 rows) per layer, halo 9 per side.
 // 12 worker warps (row quarter x channel group) + 1 MMA/weights warp, one CTA per SM; all conv
 // weights of the level (101 KB of bf16 hi|lo at C=24) stay resident in shared memory.
+//
+// What bounds it: with N = C = 24 the tensor core is limited by shared-memory operand reads (a 4 KB A
+// tile per 128x32x16 MMA), not by its math rate.  Two measures cut that traffic and hide the rest:
+//   * the 3-term split  a_hi*w_hi + a_hi*w_lo + a_lo*w_hi  is issued as TWO MMAs per K chunk:
+//     a_hi x [w_hi | w_lo] (N doubled, the epilogue adds the two column halves) and a_lo x w_hi;
+//   * the two branches are independent chains, so the MMAs of one branch run while the workers drain
+//     the other branch's accumulators (per-branch ready / accumulator mbarriers, 4 accumulators in TMEM).
+// Channel padding (C = 24 -> K = 32) is a single shared all-zero strip addressed through the descriptor's
+// leading-dimension offset, so the four activation buffers hold only real channels.
 #pragma once
 #include "conv_tc3.cuh"
 
@@ -30,16 +39,38 @@ constexpr int kLfValid = 238;              // output steps per work item
 constexpr int kLfRows = 272;               // rows of an activation buffer (time t0-9 .. t0+262)
 constexpr int kLfHalo = 9;
 
+// fp32 packed [C_in][K][C_out]  ->  [tap][group g of 8 ci][hi: N rows | lo: N rows][8 ci] bf16 (zero padded):
+// a B descriptor over 2N rows sees [w_hi | w_lo], one over N rows sees w_hi.
+__global__ void pack_tc_nc_weights_kernel(const float* __restrict__ src, int C_in, int C_out, int K, int G, int N,
+                                          __nv_bfloat16* __restrict__ dst) {
+  const size_t total = (size_t)K * G * N * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int e = r % 8; r /= 8;
+    const int n = r % N; r /= N;
+    const int g = r % G; r /= G;
+    const int k = (int)r;
+    const int ci = g * 8 + e;
+    float v = 0.f;
+    if (ci < C_in && n < C_out) v = src[((size_t)ci * K + k) * C_out + n];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const size_t base = (((size_t)k * G + g) * 2 * N + n) * 8 + e;
+    dst[base] = hi;
+    dst[base + (size_t)N * 8] = lo;
+  }
+}
+
 struct LevelFusedArgs {
   const float* sig[2];       // [B][T] raw 1-channel signals: loudness, sine
   const float* c1_w[2];      // fp32 packed [tap][C]
   const float* c1_b[2];
   const float* r1_w[2];      // fp32 [C]
   const float* r1_b[2];
-  const __nv_bfloat16* w_c2[2];   // tc2-packed (CIB = Cpad, N_tile = Npad)
+  const __nv_bfloat16* w_c2[2];   // pack_tc_nc format, G = Gp groups, N = N1
   const __nv_bfloat16* w_c4[2];
   const __nv_bfloat16* w_film[2];
-  const __nv_bfloat16* w_out;     // merged film_out, tc2-packed (CIB = 2C, N_tile = round16(2C))
+  const __nv_bfloat16* w_out;     // merged film_out, pack_tc_nc format, G = 2C/8, N = N2
   const float* b_c2[2];
   const float* b_c4[2];
   const float* b_film[2];
@@ -48,22 +79,22 @@ struct LevelFusedArgs {
   float* gb;                 // [B][T][2C]
   int C, T, B, dec;
   int n_tiles;               // ceil(T / kLfValid)
-  int Gp;                    // padded groups of a C->C conv (CIB/8)
-  int N1;                    // N tile of the C->C convs
-  int N2;                    // N tile of film_out
+  int Gp;                    // groups of a C->C conv incl. K padding (even)
+  int N1;                    // N of the C->C convs (multiple of 16, <= 32)
+  int N2;                    // N of film_out (multiple of 16, <= 64)
   float slope;
 };
 
 struct LevelFusedSmem {
-  uint32_t off_w_c2[2], off_w_c4[2], off_w_film[2], off_w_out, off_buf[3], off_sig, off_par, off_bar, total;
+  uint32_t off_w_c2[2], off_w_c4[2], off_w_film[2], off_w_out, off_buf[4], off_zero, off_sig, off_par, off_bar, total;
   uint32_t w1_bytes, w2_bytes, buf_bytes;
 };
 __host__ __device__ inline LevelFusedSmem level_fused_smem(int C, int Gp, int N1, int N2) {
   LevelFusedSmem s;
-  const uint32_t G2 = 2 * C / 8;
+  const uint32_t G = C / 8, G2 = 2 * C / 8;
   s.w1_bytes = 2u * 3u * Gp * N1 * 16u;
   s.w2_bytes = 2u * 3u * G2 * N2 * 16u;
-  s.buf_bytes = 2u * Gp * kLfRows * 16u;
+  s.buf_bytes = 2u * G * kLfRows * 16u;  // hi plane | lo plane, real channel groups only
   uint32_t off = 0;
   for (int br = 0; br < 2; ++br) {
     s.off_w_c2[br] = off; off += s.w1_bytes;
@@ -71,9 +102,10 @@ __host__ __device__ inline LevelFusedSmem level_fused_smem(int C, int Gp, int N1
     s.off_w_film[br] = off; off += s.w1_bytes;
   }
   s.off_w_out = off; off += s.w2_bytes;
-  for (int i = 0; i < 3; ++i) { s.off_buf[i] = off; off += s.buf_bytes; }
+  for (int i = 0; i < 4; ++i) { s.off_buf[i] = off; off += s.buf_bytes; }
+  s.off_zero = off; off += kLfRows * 16u;  // the shared K-padding strip (must lie above every buffer)
   s.off_sig = off; off += 2u * kLfRows * 4u;
-  s.off_par = off; off += (2u * (3u + 1u + 1u + 1u + 1u + 1u + 1u) * 32u + 64u) * 4u;  // per-branch small fp32 params
+  s.off_par = off; off += (2u * 9u * 32u + 64u) * 4u;
   off = (off + 15u) & ~15u;
   s.off_bar = off; off += 8 * 8 + 16;
   s.total = off;
@@ -91,26 +123,28 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
   const int C = p.C, G = C >> 3, Gp = p.Gp;
   const LevelFusedSmem L = level_fused_smem(C, Gp, p.N1, p.N2);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-  uint64_t* bar_ready = bars;        // workers -> MMA: the layer input in shared memory is complete (count 384)
-  uint64_t* bar_acc = bars + 1;      // [2] MMA -> workers: accumulator of M-tile 0 / 1 is complete
-  uint64_t* bar_w = bars + 3;        // weights landed
+  uint64_t* bar_ready = bars;        // [2] workers -> MMA: branch br's next layer input is complete (count 384)
+  uint64_t* bar_acc = bars + 2;      // [2][2] MMA -> workers: accumulator (branch, M-tile) is complete
+  uint64_t* bar_w = bars + 6;        // weights landed
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
   float* s_sig = reinterpret_cast<float*>(smem + L.off_sig);   // [2][kLfRows]: index i <-> time t0 - 10 + i
   float* s_par = reinterpret_cast<float*>(smem + L.off_par);
   float* s_bout = s_par + 2 * kLfParPerBranch * 32;
-  const uint32_t strip = kLfRows * 16u, plane = (uint32_t)Gp * strip;
+  const uint32_t strip = kLfRows * 16u, plane = (uint32_t)G * strip;
+  const uint32_t buf_off0 = L.off_buf[0], buf_bytes = L.buf_bytes;
+  // buffers: X_br = buffer 2*br (a1, then y), Y_br = buffer 2*br+1 (a2, then h)
 
   if (tid == 0) {
     mbar_init(bar_ready, kLfWorkers);
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_acc + 1, 1);
+    mbar_init(bar_ready + 1, kLfWorkers);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_acc + i, 1);
     mbar_init(bar_w, 1);
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(s_tmem, 128);
-  // zero the activation buffers once: the K-padding groups are never written again and must stay finite
-  for (uint32_t i = tid; i < 3u * L.buf_bytes / 16u; i += kLfThreads)
-    reinterpret_cast<uint4*>(smem + L.off_buf[0])[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 12) tmem_alloc(s_tmem, 256);
+  // zero the K-padding strip (never written again) and the buffers (stale rows must stay finite)
+  for (uint32_t i = tid; i < (4u * buf_bytes + strip) / 16u; i += kLfThreads)
+    reinterpret_cast<uint4*>(smem + buf_off0)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 2 * kLfParPerBranch * 32 + 64; i += kLfThreads) {
     float v = 0.f;
     if (i < 2 * kLfParPerBranch * 32) {
@@ -149,67 +183,81 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
       }
       bulk_g2s(smem + L.off_w_out, p.w_out, L.w2_bytes, bar_w);
       mbar_wait2(bar_w, 0);
-      const uint32_t idesc1 = umma_idesc_bf16(128, p.N1), idesc2 = umma_idesc_bf16(128, p.N2);
-      const uint32_t buf_addr[3] = {smem_u32(smem + L.off_buf[0]), smem_u32(smem + L.off_buf[1]),
-                                    smem_u32(smem + L.off_buf[2])};
-      uint32_t ready_phase = 0;
-      // one C->C layer: A = buffer `src`, output window starts at time offset s (row s + 9), dilation d
-      auto issue_layer = [&](uint32_t a_base, uint32_t w_addr, int s, int d) {
-        mbar_wait2(bar_ready, ready_phase);
-        ready_phase ^= 1u;
+      const uint32_t idesc_c = umma_idesc_bf16(128, 2 * p.N1), idesc_h = umma_idesc_bf16(128, p.N1);
+      const uint32_t idesc_oc = umma_idesc_bf16(128, 2 * p.N2), idesc_oh = umma_idesc_bf16(128, p.N2);
+      const uint32_t buf0 = smem_u32(smem + buf_off0), zero_addr = smem_u32(smem + L.off_zero);
+      const uint32_t w_base = smem_u32(smem);
+      uint32_t ready_phase0 = 0u, ready_phase1 = 0u;
+      auto mk = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+      // Descriptor words: bits [0,14) of the low word = start address >> 4, bits [16,30) = leading-dimension
+      // byte offset >> 4 (distance between the two 8-channel columns of a K=16 slice); high word = SBO | version.
+      auto desc_lo = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
+      const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
+      // one C->C layer of branch br: A = buffer `src` (0 = X, 1 = Y), window start s, dilation d
+      auto issue_layer = [&](int br, int src, uint32_t w_addr, int s, int d) {
+        const uint32_t row0 = (uint32_t)(s + kLfHalo - d);
+        const uint32_t a_base = buf0 + (uint32_t)(2 * br + src) * buf_bytes;
+        const uint32_t b_grp = 2u * (uint32_t)p.N1 * 16u;  // one ci group of B: hi rows | lo rows
+        if (br == 0) {
+          mbar_wait2(bar_ready, ready_phase0);
+          ready_phase0 ^= 1u;
+        } else {
+          mbar_wait2(bar_ready + 1, ready_phase1);
+          ready_phase1 ^= 1u;
+        }
         tc_fence_after();
-        const uint32_t b_strip = (uint32_t)p.N1 * 16u, b_half = 3u * Gp * b_strip;
         for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t d_tmem = tmem + (uint32_t)mt * 64u;
+          const uint32_t d_tmem = tmem + (uint32_t)(2 * br + mt) * 64u;
+          uint32_t accum = 0u;
+#pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const uint32_t row = (uint32_t)(s + kLfHalo + (k - 1) * d + 128 * mt);
+            const uint32_t rbytes = (row0 + (uint32_t)(k * d + 128 * mt)) * 16u;
             for (int kc = 0; kc < Gp / 2; ++kc) {
-              const uint32_t a_off = 2u * kc * strip + row * 16u;
-              const uint32_t b_off = ((uint32_t)k * Gp + 2u * kc) * b_strip;
-              const uint64_t a_hi = umma_desc(a_base + a_off, strip, 128);
-              const uint64_t a_lo = umma_desc(a_base + plane + a_off, strip, 128);
-              const uint64_t b_hi = umma_desc(w_addr + b_off, b_strip, 128);
-              const uint64_t b_lo = umma_desc(w_addr + b_half + b_off, b_strip, 128);
-              const uint32_t accum = (k == 0 && kc == 0) ? 0u : 1u;
-              umma_bf16(d_tmem, a_lo, b_hi, idesc1, accum);
-              umma_bf16(d_tmem, a_hi, b_lo, idesc1, 1u);
-              umma_bf16(d_tmem, a_hi, b_hi, idesc1, 1u);
+              const int g0 = 2 * kc, g1 = g0 + 1;
+              const uint32_t a0 = a_base + (uint32_t)g0 * strip + rbytes;
+              // second 8-channel column: the next real group, or the shared zero strip for the K padding
+              const uint32_t a1h = g1 < G ? a0 + strip : zero_addr + rbytes;
+              const uint32_t a1l = g1 < G ? a0 + plane + strip : zero_addr + rbytes;
+              const uint32_t b_addr = w_addr + ((uint32_t)k * Gp + g0) * b_grp;
+              const uint64_t A_hi = mk(desc_lo(a0, a1h - a0), desc_hi);
+              const uint64_t A_lo = mk(desc_lo(a0 + plane, a1l - (a0 + plane)), desc_hi);
+              const uint64_t Bd = mk(desc_lo(b_addr, b_grp), desc_hi);
+              umma_bf16(d_tmem, A_hi, Bd, idesc_c, accum);  // a_hi x [w_hi | w_lo]  -> columns [0, 2N)
+              umma_bf16(d_tmem, A_lo, Bd, idesc_h, 1u);     // a_lo x w_hi           -> columns [0, N)
+              accum = 1u;
             }
           }
-          umma_commit(bar_acc + mt);
+          umma_commit(bar_acc + 2 * br + mt);
         }
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        for (int br = 0; br < 2; ++br) {
-          const uint32_t hbuf = buf_addr[1 + br];
-          issue_layer(buf_addr[0], smem_u32(smem + L.off_w_c2[br]), -6, 2);    // a1 (buf 0) -> a2 (buf 1+br)
-          issue_layer(hbuf, smem_u32(smem + L.off_w_c4[br]), -2, 4);           // a2 -> y (buf 0)
-          issue_layer(buf_addr[0], smem_u32(smem + L.off_w_film[br]), -1, 1);  // y -> h (buf 1+br)
-        }
-        // merged film_out over the virtual channel concat [h_lft (buf 1) | h_sine (buf 2)]
-        mbar_wait2(bar_ready, ready_phase);
-        ready_phase ^= 1u;
+        for (int br = 0; br < 2; ++br) issue_layer(br, 0, w_base + L.off_w_c2[br], -6, 2);    // a1 (X) -> a2 (Y)
+        for (int br = 0; br < 2; ++br) issue_layer(br, 1, w_base + L.off_w_c4[br], -2, 4);    // a2 (Y) -> y  (X)
+        for (int br = 0; br < 2; ++br) issue_layer(br, 0, w_base + L.off_w_film[br], -1, 1);  // y  (X) -> h  (Y)
+        // merged film_out over the virtual channel concat [h_lft (Y_0) | h_sine (Y_1)]
+        mbar_wait2(bar_ready, ready_phase0);
+        ready_phase0 ^= 1u;
+        mbar_wait2(bar_ready + 1, ready_phase1);
+        ready_phase1 ^= 1u;
         tc_fence_after();
-        const uint32_t G2 = 2u * G, b_strip = (uint32_t)p.N2 * 16u, b_half = 3u * G2 * b_strip;
-        const uint32_t w_addr = smem_u32(smem + L.off_w_out);
+        const uint32_t G2 = 2u * G, b_grp = 2u * (uint32_t)p.N2 * 16u;
+        const uint32_t w_addr = w_base + L.off_w_out;
         for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t d_tmem = tmem + (uint32_t)mt * 64u;
+          const uint32_t d_tmem = tmem + (uint32_t)mt * 128u;
+          uint32_t accum = 0u;
           for (int k = 0; k < 3; ++k) {
-            const uint32_t row = (uint32_t)(0 + kLfHalo + (k - 1) + 128 * mt);
+            const uint32_t rbytes = (uint32_t)(kLfHalo + (k - 1) + 128 * mt) * 16u;
             for (uint32_t kc = 0; kc < G2 / 2; ++kc) {
               const uint32_t v0 = 2u * kc, v1 = v0 + 1;
-              const uint32_t addr0 = buf_addr[1 + (v0 >= (uint32_t)G)] + (v0 % G) * strip + row * 16u;
-              const uint32_t addr1 = buf_addr[1 + (v1 >= (uint32_t)G)] + (v1 % G) * strip + row * 16u;
-              const uint32_t lbo = addr1 - addr0;
-              const uint32_t b_off = ((uint32_t)k * G2 + v0) * b_strip;
-              const uint64_t a_hi = umma_desc(addr0, lbo, 128);
-              const uint64_t a_lo = umma_desc(addr0 + plane, lbo, 128);
-              const uint64_t b_hi = umma_desc(w_addr + b_off, b_strip, 128);
-              const uint64_t b_lo = umma_desc(w_addr + b_half + b_off, b_strip, 128);
-              const uint32_t accum = (k == 0 && kc == 0) ? 0u : 1u;
-              umma_bf16(d_tmem, a_lo, b_hi, idesc2, accum);
-              umma_bf16(d_tmem, a_hi, b_lo, idesc2, 1u);
-              umma_bf16(d_tmem, a_hi, b_hi, idesc2, 1u);
+              const uint32_t a0 = buf0 + (v0 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v0 % G) * strip + rbytes;
+              const uint32_t a1 = buf0 + (v1 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v1 % G) * strip + rbytes;
+              const uint32_t b_addr = w_addr + ((uint32_t)k * G2 + v0) * b_grp;
+              const uint64_t A_hi = mk(desc_lo(a0, a1 - a0), desc_hi);
+              const uint64_t A_lo = mk(desc_lo(a0 + plane, a1 - a0), desc_hi);
+              const uint64_t Bd = mk(desc_lo(b_addr, b_grp), desc_hi);
+              umma_bf16(d_tmem, A_hi, Bd, idesc_oc, accum);
+              umma_bf16(d_tmem, A_lo, Bd, idesc_oh, 1u);
+              accum = 1u;
             }
           }
           umma_commit(bar_acc + mt);
@@ -219,7 +267,8 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
   } else {
     // ================= workers =================
     const int q = warp & 3, gsel = warp >> 2;  // TMEM lane quarter; channel group select (0..2)
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.n_tiles, t0 = (item - b * p.n_tiles) * kLfValid;
       // ---- raw signal windows of both branches ----
@@ -229,52 +278,58 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         s_sig[i] = (t >= 0 && t < p.T) ? __ldg(p.sig[br] + (long long)b * p.T + t) : 0.f;
       }
       named_bar_sync(1, kLfWorkers);
+      // ---- a1 = Conv3_d1(lrelu(x)) on the CUDA cores, stored as lrelu(a1): rows time t0-8 .. t0+247 ----
       for (int br = 0; br < 2; ++br) {
         const float* sg = s_sig + br * kLfRows;
         const float* par = s_par + br * kLfParPerBranch * 32;
-        // ---- a1 = Conv3_d1(lrelu(x)) on the CUDA cores, stored as lrelu(a1): rows time t0-8 .. t0+247 ----
-        {
-          uint8_t* dst = smem + L.off_buf[0];
-          for (int idx = tid; idx < 256 * G; idx += kLfWorkers) {
-            const int g = idx >> 8, r = idx & 255;
-            const int tau = r - 8, t = t0 + tau;
-            float v[8];
+        uint8_t* dst = smem + buf_off0 + (uint32_t)(2 * br) * buf_bytes;
+        for (int idx = tid; idx < 256 * G; idx += kLfWorkers) {
+          const int g = idx >> 8, r = idx & 255;
+          const int tau = r - 8, t = t0 + tau;
+          float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-            if (t >= 0 && t < p.T) {
-              const float x0 = sg[tau + 9], x1 = sg[tau + 10], x2 = sg[tau + 11];
-              const float l0 = fmaxf(x0, x0 * p.slope), l1 = fmaxf(x1, x1 * p.slope), l2 = fmaxf(x2, x2 * p.slope);
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          if (t >= 0 && t < p.T) {
+            const float x0 = sg[tau + 9], x1 = sg[tau + 10], x2 = sg[tau + 11];
+            const float l0 = fmaxf(x0, x0 * p.slope), l1 = fmaxf(x1, x1 * p.slope), l2 = fmaxf(x2, x2 * p.slope);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int c = g * 8 + e;
-                float y = par[kLfC1B * 32 + c];
-                y = fmaf(par[(kLfC1W + 0) * 32 + c], l0, y);
-                y = fmaf(par[(kLfC1W + 1) * 32 + c], l1, y);
-                y = fmaf(par[(kLfC1W + 2) * 32 + c], l2, y);
-                v[e] = fmaxf(y, y * p.slope);
-              }
+            for (int e = 0; e < 8; ++e) {
+              const int c = g * 8 + e;
+              float y = par[kLfC1B * 32 + c];
+              y = fmaf(par[(kLfC1W + 0) * 32 + c], l0, y);
+              y = fmaf(par[(kLfC1W + 1) * 32 + c], l1, y);
+              y = fmaf(par[(kLfC1W + 2) * 32 + c], l2, y);
+              v[e] = fmaxf(y, y * p.slope);
             }
-            split_store(dst + (uint32_t)g * strip + (uint32_t)(tau + kLfHalo) * 16u, plane, v);
           }
-          fence_proxy_async();
-          mbar_arrive(bar_ready);
+          split_store(dst + (uint32_t)g * strip + (uint32_t)(tau + kLfHalo) * 16u, plane, v);
         }
-        // ---- three tensor-core layers: TMEM -> (bias, residual, activation, zero padding) -> bf16 hi|lo -> smem ----
-        for (int layer = 0; layer < 3; ++layer) {
-          const int s = layer == 0 ? -6 : (layer == 1 ? -2 : -1);
-          uint8_t* dst = smem + (layer == 1 ? L.off_buf[0] : L.off_buf[1 + br]);
+        fence_proxy_async();
+        mbar_arrive(bar_ready + br);
+      }
+      // ---- three tensor-core layers per branch, branches interleaved:
+      //      TMEM -> (hi + lo halves, bias, residual, activation, zero padding) -> bf16 hi|lo -> smem ----
+      for (int layer = 0; layer < 3; ++layer) {
+        const int s = layer == 0 ? -6 : (layer == 1 ? -2 : -1);
+        for (int br = 0; br < 2; ++br) {
+          const float* sg = s_sig + br * kLfRows;
+          const float* par = s_par + br * kLfParPerBranch * 32;
+          uint8_t* dst = smem + buf_off0 + (uint32_t)(2 * br + (layer == 1 ? 0 : 1)) * buf_bytes;
           const float* bias = par + (layer == 0 ? kLfBC2 : (layer == 1 ? kLfBC4 : kLfBFilm)) * 32;
+          const uint32_t ph = br == 0 ? acc_phase0 : acc_phase1;
           for (int mt = 0; mt < 2; ++mt) {
-            mbar_wait2(bar_acc + mt, acc_phase);
+            mbar_wait2(bar_acc + 2 * br + mt, ph);
             tc_fence_after();
             const int tau = s + 128 * mt + q * 32 + lane, t = t0 + tau;
             const bool in_seq = t >= 0 && t < p.T;
+            const uint32_t tbase = tmem + (uint32_t)(2 * br + mt) * 64u + lane_addr;
             for (int g = gsel; g < G; g += 3) {
-              float v[8];
-              tmem_ld8(tmem + (uint32_t)mt * 64u + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), v);
+              float v[8], w[8];
+              tmem_ld8(tbase + (uint32_t)(g * 8), v);
+              tmem_ld8(tbase + (uint32_t)(p.N1 + g * 8), w);
               if (in_seq) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += bias[g * 8 + e];
+                for (int e = 0; e < 8; ++e) v[e] += w[e] + bias[g * 8 + e];
                 if (layer == 1) {  // + Conv1x1(x), then the level output y (kept raw for the FiLM conv)
                   const float x = sg[tau + 10];
 #pragma unroll
@@ -295,41 +350,43 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
               split_store(dst + (uint32_t)g * strip + (uint32_t)(tau + kLfHalo) * 16u, plane, v);
             }
           }
-          acc_phase ^= 1u;
+          if (br == 0) acc_phase0 ^= 1u;
+          else acc_phase1 ^= 1u;
           fence_proxy_async();
           tc_fence_before();
-          // (h of the first branch is consumed only by film_out: its completion rides on the next arrive)
-          if (!(layer == 2 && br == 0)) mbar_arrive(bar_ready);
+          mbar_arrive(bar_ready + br);
         }
       }
       // ---- merged film_out: gamma | beta rows straight to HBM ----
       for (int mt = 0; mt < 2; ++mt) {
-        mbar_wait2(bar_acc + mt, acc_phase);
+        mbar_wait2(bar_acc + mt, acc_phase0);
         tc_fence_after();
         const int tau = 128 * mt + q * 32 + lane, t = t0 + tau;
         const bool ok = tau < kLfValid && t < p.T;
+        const uint32_t tbase = tmem + (uint32_t)mt * 128u + lane_addr;
         for (int g = gsel; g < 2 * G; g += 3) {
-          float v[8];
-          tmem_ld8(tmem + (uint32_t)mt * 64u + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 8), v);
+          float v[8], w[8];
+          tmem_ld8(tbase + (uint32_t)(g * 8), v);
+          tmem_ld8(tbase + (uint32_t)(p.N2 + g * 8), w);
           if (ok) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += s_bout[g * 8 + e];
+            for (int e = 0; e < 8; ++e) v[e] += w[e] + s_bout[g * 8 + e];
             float4* op = reinterpret_cast<float4*>(p.gb + ((long long)b * p.T + t) * (2 * C) + g * 8);
             op[0] = make_float4(v[0], v[1], v[2], v[3]);
             op[1] = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
       }
-      acc_phase ^= 1u;
+      acc_phase0 ^= 1u;
       tc_fence_before();
-      // (the next item's first MMA is gated by bar_ready, which every worker arrives on only after this point)
+      // (the next item's first MMAs are gated by bar_ready, which every worker arrives on only after this point)
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 12) {
     __syncwarp();
-    tmem_dealloc(tmem, 128);
+    tmem_dealloc(tmem, 256);
   }
 }
 
