@@ -92,6 +92,14 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity) {
       "r"(parity), "r"(0x989680u)
       : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running.  launch_dependents lets OUR successor start early
+// (every CTA issues it at once: all grids here are single-wave, so nothing of this kernel is left to schedule);
+// griddep_wait blocks until the predecessor grid has completed and its writes are visible -- every thread calls
+// it before its first access to activations / workspace (weights and parameters are not produced by kernels).
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
   uint32_t acc_stride = 32;
   while (acc_stride < (uint32_t)a.N_tile) acc_stride <<= 1;
 
+  griddep_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(bars + kBarBFull + i, 1);
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         }
       }
     };
+    griddep_wait();  // first access to the predecessor's output
     uint32_t pa_pos = 0;
     auto convert_chunk = [&](const Cursor& q, const float4 (&d)[CH][2], uint32_t live) {
       const uint32_t aslot = pa_pos % (uint32_t)c.a_slots, ause = pa_pos / (uint32_t)c.a_slots;
@@ -408,6 +410,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         }
       }
     };
+    griddep_wait();  // before the first operand load and the first store
     load_ops(first, 0);
     int it = 0;
     for (int m = first; m < n_m; m += step, ++it) {

@@ -41,6 +41,7 @@ struct ConvW {  // packed [C_in][K][C_out] + bias[C_out], device
   TcW tc2;  // copy tiled for the persistent channels-last kernel (conv_tc2.cuh)
   int tc2_resident = 0;
   int ctx_dil = 1, ctx_up = 1;  // how the generator uses this conv (dilation, upsampling factor of its input)
+  int ctx_wide = 0;             // conditioning conv: prefer one wide N tile
   const __nv_bfloat16* wnc = nullptr;  // [tap][group][hi|lo rows][8] copy for the fused level kernel
   int nc_G = 0, nc_N = 0;
 };
@@ -70,7 +71,9 @@ static bool tc2_plan(int C_in, int C_out, int K, ConvW* cw) {
   if (C_out % 8 != 0 || C_in % 8 != 0 || C_in < 8) return false;
   const int c16 = (C_in + 15) / 16 * 16;
   const int n16 = (C_out + 15) / 16 * 16;
-  t->n_ntiles = (n16 + 127) / 128;
+  // conditioning convs (two branches per launch, or 2C outputs) take N tiles of up to 256 columns so the A window
+  // is converted once; stage convs (one problem, few time tiles) keep <= 128 columns for twice the CTAs
+  t->n_ntiles = cw->ctx_wide ? (n16 + 255) / 256 : (n16 + 127) / 128;
   t->N_tile = ((n16 + t->n_ntiles - 1) / t->n_ntiles + 15) / 16 * 16;
   t->N_alloc = 32;
   while (t->N_alloc < t->N_tile) t->N_alloc *= 2;
@@ -660,6 +663,24 @@ static Tc2Args tc2_args(const Ctx& c, const ConvW& w, const float* in, int in_ld
   return a;
 }
 
+// Launch with programmatic stream serialization: the kernel may begin (barrier / TMEM setup, weight streaming)
+// while its predecessor drains; it orders itself with griddepcontrol.wait before touching activations.
+template <typename Kern, typename Arg>
+static void launch_pdl(Kern kern, dim3 grid, int block, size_t smem, cudaStream_t stream, const Arg& arg) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, arg);
+}
+
 // Launch 1 or 2 problems of identical shape and flags (the two conditioning branches) as one persistent grid
 // of the warp-specialised kernel; problem 1 is expressed as pointer deltas against problem 0.
 static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, int n_prob, const char* name) {
@@ -703,8 +724,8 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   per_group = per_group < 1 ? 1 : per_group;
   per_group = per_group > items ? items : per_group;
   const dim3 grid(per_group * groups);
-  if (K == 3) conv_tc3_kernel<3><<<grid, kTc3Threads, cfg.total, c.stream>>>(L);
-  else conv_tc3_kernel<1><<<grid, kTc3Threads, cfg.total, c.stream>>>(L);
+  if (K == 3) launch_pdl(conv_tc3_kernel<3>, grid, kTc3Threads, cfg.total, c.stream, L);
+  else launch_pdl(conv_tc3_kernel<1>, grid, kTc3Threads, cfg.total, c.stream, L);
   double flops = 0, elems = 0;
   for (int i = 0; i < n_prob; ++i) {
     const Tc2Args& a = p[i];
@@ -791,7 +812,7 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
       fa.slope = c.slope;
       const int items = B * fa.n_tiles;
       const int grid = items < h->num_sms ? items : h->num_sms;
-      level0_fused_kernel<<<grid, kLfThreads, LF.total, stream>>>(fa);
+      launch_pdl(level0_fused_kernel, dim3(grid), kLfThreads, LF.total, stream, fa);
       const double BT = (double)B * T_l;
       c.launched("fused_level", 2.0 * BT * C * (2.0 * (3 + 1 + 9.0 * C) + 2.0 * 9 * C + 12.0 * C),
                  4.0 * (2 * BT + 2 * BT * C / dec + 2 * BT * C));
@@ -1052,6 +1073,8 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
       add_conv(h->level[l].c4[br], p + ".downsample_block.6", C, C, 3);
       h->level[l].c2[br].ctx_dil = 2;
       h->level[l].c4[br].ctx_dil = 4;
+      for (ConvW* cw : {&h->level[l].r1[br], &h->level[l].c1[br], &h->level[l].c2[br], &h->level[l].c4[br]})
+        cw->ctx_wide = 1;
       ci = C;
     }
   }
@@ -1060,10 +1083,14 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
       const int C = h->lvl_c[l];
       const std::string p = fn[br] + std::to_string(l);
       add_conv(h->level[l].film[br], p + ".conv", C, C, 3);
+      h->level[l].film[br].ctx_wide = 1;
       add_info(p + ".conv_scale", (int64_t)C * C * 3, C);
       add_info(p + ".conv_shift", (int64_t)C * C * 3, C);
     }
-  for (int l = 0; l < n; ++l) add_conv(h->level[l].film_out, "", 2 * h->lvl_c[l], 2 * h->lvl_c[l], 3, false);
+  for (int l = 0; l < n; ++l) {
+    add_conv(h->level[l].film_out, "", 2 * h->lvl_c[l], 2 * h->lvl_c[l], 3, false);
+    h->level[l].film_out.ctx_wide = 1;
+  }
   add_conv(h->last, "conv_last", cfg->out_channels, cfg->mid_channels[n - 1], 1);
 
   h->store_floats = off;

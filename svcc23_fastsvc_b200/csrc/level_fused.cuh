@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
   const uint32_t buf_off0 = L.off_buf[0], buf_bytes = L.buf_bytes;
   // buffers: X_br = buffer 2*br (a1, then y), Y_br = buffer 2*br+1 (a2, then h)
 
+  griddep_launch_dependents();
   if (tid == 0) {
     mbar_init(bar_ready, kLfWorkers);
     mbar_init(bar_ready + 1, kLfWorkers);
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
     const int q = warp & 3, gsel = warp >> 2;  // TMEM lane quarter; channel group select (0..2)
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    griddep_wait();  // the outputs of this kernel may still be read by the previous forward's kernels
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.n_tiles, t0 = (item - b * p.n_tiles) * kLfValid;
       // ---- raw signal windows of both branches ----
