@@ -74,6 +74,17 @@ struct Tc2Batch {  // up to 2 independent problems of identical tiling in one la
   int B, m_tiles;  // items per problem and N tile = B * m_tiles
 };
 
+// Blocked channels-last activation layout of the tensor-core forward: [B][ceil(T/32)][ld/4][32 steps][4 channels].
+// 32 consecutive time steps of one 4-channel group are 512 contiguous bytes, so a warp whose lanes own
+// consecutive time steps (the TMEM epilogue, the A-window staging) touches whole 128-byte lines with every
+// 128-bit access -- a plain [T][C] row layout costs one line per lane there.  Offsets are in floats; a channel
+// offset co (multiple of 4) is folded into a base pointer as (co / 4) * 128.
+__host__ __device__ inline long long ntc_tp(int T) { return (long long)((T + 31) / 32) * 32; }
+__host__ __device__ inline long long ntc_row(long long Tp, int ld, int b, int t) {
+  return ((long long)b * Tp + (t & ~31)) * ld + (t & 31) * 4;
+}
+__host__ __device__ inline long long ntc_col(int co) { return (long long)(co >> 2) * 128 + (co & 3); }
+
 constexpr int kTc2Threads = 256;
 constexpr int kTc2M = 128;
 
@@ -648,7 +659,7 @@ __global__ void __launch_bounds__(256) spk_project_all_kernel(const float* __res
   }
 }
 
-// conv_last (Conv1d1x1, fastsvc.py:301,330) from channels-last x [B*T][C] to (B, C_out, T):
+// conv_last (Conv1d1x1, fastsvc.py:301,330) from blocked channels-last x to (B, C_out, T):
 // one thread per time step.  w is the packed fp32 layout [C][C_out].
 __global__ void __launch_bounds__(256) conv_last_ntc_kernel(const float* __restrict__ x, int C, int T, long long BT,
                                                             const float* __restrict__ w, const float* __restrict__ bias,
@@ -657,11 +668,11 @@ __global__ void __launch_bounds__(256) conv_last_ntc_kernel(const float* __restr
   if (i >= BT) return;
   const long long b = i / T;
   const int t = (int)(i - b * T);
-  const float4* xp = reinterpret_cast<const float4*>(x + i * C);
+  const float4* xp = reinterpret_cast<const float4*>(x + ntc_row(ntc_tp(T), C, (int)b, t));
   for (int co = 0; co < C_out; ++co) {
     float acc = __ldg(bias + co);
     for (int c4 = 0; c4 < C / 4; ++c4) {
-      const float4 v = __ldg(xp + c4);
+      const float4 v = __ldg(xp + 32 * c4);
       const float* wp = w + (long long)(4 * c4) * C_out + co;
       acc = fmaf(v.x, __ldg(wp), acc);
       acc = fmaf(v.y, __ldg(wp + C_out), acc);

@@ -52,6 +52,29 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// bf16 hi|lo split of 8 fp32 values, stored as two 16-byte chunks (32-bit shared-space addresses)
+__device__ __forceinline__ void split_store_s(uint32_t addr, uint32_t plane, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  sts128(addr, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+  sts128(addr + plane, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+}
+
 enum {  // mbarrier indices
   kBarBFull = 0,     // [2] streamed weight block landed
   kBarBEmpty = 2,    // [2] MMAs that read it completed
@@ -103,7 +126,9 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c) {
   return false;
 }
 
-template <int K>
+// NH4: float4 units per epilogue thread and sub-tile, fixed at compile time (3 = the 24-channel sub-tile every
+// conv of the YAML generator uses) or 0 = decided at run time (any multiple-of-8 channel count).
+template <int K, int NH4>
 __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw;
@@ -231,6 +256,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
   } else if (warp < 2 + kTc3XformWarps) {
     // =============================== TRANSFORM ===============================
     const int tt = tid - 64;
+    const uint32_t smem_base = smem_u32(smem);
     const float* in = a.in + prob * L.d_in;  // gen mode: 1-channel signal [B][T_in]
     const float* gen_w = gen ? a.gen_w + prob * L.d_gen_w : nullptr;
     const float* gen_b = gen ? a.gen_b + prob * L.d_gen_b : nullptr;
@@ -238,21 +264,29 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
     const int cpad = (a.C_in + 7) / 8 * 8;
     const int Gb = a.CIB >> 3;  // groups of 8 channels per (padded) ci block
     const uint32_t strip = (uint32_t)W * 16u, plane = (uint32_t)Gb * strip;
-    const uint32_t gb_magic = 0xFFFFFFFFu / (uint32_t)Gb + 1u;    // exact quotients below 2^16
+    const uint32_t w_magic = 0xFFFFFFFFu / (uint32_t)W + 1u;      // exact quotients below 2^16
+    const long long Tp_in = ntc_tp(a.T_in);
     const uint32_t up_magic = 0xFFFFFFFFu / (uint32_t)a.up + 1u;
     const int items = W * Gb;
     constexpr int CH = kTc3ChunkItems, CHUNK = CH * kTc3XformThreads;
     const int n_chunks = (items + CHUNK - 1) / CHUNK;
 
     struct Cursor {
-      int m, blk, ch, it;
+      int m, blk, ch, it, b, tile;  // (b, tile) track m without a division per chunk
     };
+    const int step_b = step / c.m_tiles, step_t = step - step_b * c.m_tiles;
     auto advance = [&](Cursor& q) {
       if (++q.ch == n_chunks) {
         q.ch = 0;
         if (++q.blk == a.n_blk) {
           q.blk = 0;
           q.m += step;
+          q.b += step_b;
+          q.tile += step_t;
+          if (q.tile >= c.m_tiles) {
+            q.tile -= c.m_tiles;
+            ++q.b;
+          }
           ++q.it;
         }
       }
@@ -261,7 +295,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
     auto load_chunk = [&](const Cursor& q, float4 (&d)[CH][2], uint32_t& live) {
       live = 0;
       if (q.m >= n_m) return;
-      const int b = q.m / c.m_tiles, t0 = (q.m - b * c.m_tiles) * kTc2M;
+      const int b = q.b, t0 = q.tile * kTc2M;
       const int ci0 = q.blk * a.CIB;
       // InstanceNorm affine of this tile's utterance, written one chunk early.  Three buffers: the write for
       // tile i+3 follows the named barrier of tile i+1, which every thread reaches only after converting tile i.
@@ -276,7 +310,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
       for (int j = 0; j < CH; ++j) {
         const int idx = q.ch * CHUNK + j * kTc3XformThreads + tt;
         if (idx < items) {
-          const int r = (int)__umulhi((uint32_t)idx, gb_magic), g = idx - r * Gb;
+          const int g = (int)__umulhi((uint32_t)idx, w_magic), r = idx - g * W;  // lanes <-> consecutive steps
           const int u = t0 - halo + r, ch = ci0 + g * 8;
           if (u >= 0 && u < a.T_out && ch < a.C_in) {
             live |= 1u << j;
@@ -287,9 +321,9 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
               d[j][0].z = u + 1 < a.T_out ? __ldg(x + 1) : 0.f;
             } else {
               const int src = (a.up == 1 ? u : (int)__umulhi((uint32_t)u, up_magic)) * a.down;
-              const float4* p = reinterpret_cast<const float4*>(in + ((long long)b * a.T_in + src) * a.in_ld + ch);
+              const float4* p = reinterpret_cast<const float4*>(in + ntc_row(Tp_in, a.in_ld, b, src) + (ch >> 2) * 128);
               d[j][0] = __ldg(p);
-              d[j][1] = __ldg(p + 1);
+              d[j][1] = __ldg(p + 32);
             }
           }
         }
@@ -303,15 +337,15 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
         if (q.blk == 0 && a.pre_a) named_bar_sync(1, kTc3XformThreads);  // s_pa of this tile is complete
       }
-      uint8_t* sA = smem + c.off_a + aslot * c.a_bytes;
-      const float* s_pa = s_pa_base + (q.it % 3) * 2 * cpad;
-      const float* s_pc = s_pa + cpad;
+      const uint32_t sA = smem_base + c.off_a + aslot * c.a_bytes;
+      const uint32_t s_pa = smem_base + c.off_pa + (uint32_t)((q.it % 3) * 2 * cpad) * 4u;
+      const uint32_t s_pc = s_pa + (uint32_t)cpad * 4u;
       const int ci0 = q.blk * a.CIB;
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const int idx = q.ch * CHUNK + j * kTc3XformThreads + tt;
         if (idx < items) {
-          const int r = (int)__umulhi((uint32_t)idx, gb_magic), g = idx - r * Gb;
+          const int g = (int)__umulhi((uint32_t)idx, w_magic), r = idx - g * W;
           const int ch = ci0 + g * 8;
           float v[8];
 #pragma unroll
@@ -333,9 +367,8 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
               v[0] = d[j][0].x; v[1] = d[j][0].y; v[2] = d[j][0].z; v[3] = d[j][0].w;
               v[4] = d[j][1].x; v[5] = d[j][1].y; v[6] = d[j][1].z; v[7] = d[j][1].w;
               if (a.pre_a) {
-                const float4* pa4 = reinterpret_cast<const float4*>(s_pa + ch);
-                const float4* pc4 = reinterpret_cast<const float4*>(s_pc + ch);
-                const float4 a0 = pa4[0], a1 = pa4[1], c0 = pc4[0], c1 = pc4[1];
+                const float4 a0 = lds128f(s_pa + (uint32_t)ch * 4u), a1 = lds128f(s_pa + (uint32_t)ch * 4u + 16u);
+                const float4 c0 = lds128f(s_pc + (uint32_t)ch * 4u), c1 = lds128f(s_pc + (uint32_t)ch * 4u + 16u);
                 v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
                 v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
                 v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
@@ -347,7 +380,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
               for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], v[e] * a.slope);  // slope in (0, 1)
             }
           }
-          split_store(sA + (uint32_t)g * strip + (uint32_t)r * 16u, plane, v);
+          split_store_s(sA + (uint32_t)g * strip + (uint32_t)r * 16u, plane, v);
         }
       }
       if (q.ch == n_chunks - 1) {
@@ -357,7 +390,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
       }
     };
     // software pipeline over the chunk sequence: chunk k+1 is in flight while chunk k is converted
-    Cursor cur{first, 0, 0, 0};
+    Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
     float4 d0[CH][2], d1[CH][2];
     uint32_t live0, live1;
     load_chunk(cur, d0, live0);
@@ -384,63 +417,86 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
     const float* gres_x = a.gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
     float* raw = a.raw ? a.raw + prob * L.d_raw : nullptr;
     float* out = a.out ? a.out + prob * L.d_out : nullptr;
-    const bool has_film = a.gamma != nullptr;
-    float* scr = reinterpret_cast<float*>(smem + c.off_scr) + ew * 32 * c.scr_pitch;
+    const bool has_film = a.gamma != nullptr, has_res = res != nullptr, has_stats = a.stats != nullptr;
+    const uint32_t scr = smem_u32(smem + c.off_scr) + (uint32_t)(ew * 32 * c.scr_pitch) * 4u;
+    const uint32_t scr_row = scr + (uint32_t)(lane * c.scr_pitch) * 4u;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int step_b = step / c.m_tiles, step_t = step - step_b * c.m_tiles;
+    const int rl = q * 32 + lane;  // row of this thread inside the tile
+    const long long Tp_out = ntc_tp(a.T_out);
+
+    // channels of this thread in sub-tile `sub`: nh (multiple of 4), starting at column sub*nsub + h*nh
+    auto unit_nh = [&](int sub) { return NH4 ? 4 * NH4 : (min(c.nsub, nvalid - sub * c.nsub) >> 1); };
 
     // operands of one (tile, sub-tile) unit for this thread: requested one unit ahead of their use
     float4 o_res[4], o_ga[4], o_be[4];
     float o_gx = 0.f;
-    auto load_ops = [&](int m, int sub) {
-      if (m >= n_m) return;
-      const int b = m / c.m_tiles, t0 = (m - b * c.m_tiles) * kTc2M;
-      const int t = t0 + q * 32 + lane;
+    auto load_ops = [&](int b, int tile, int sub) {
+      const int t = tile * kTc2M + rl;
       if (t >= a.T_out) return;
-      const long long row = (long long)b * a.T_out + t;
-      const int nh = min(c.nsub, nvalid - sub * c.nsub) >> 1;
+      const int nh = unit_nh(sub);
       const int co = co_tile + sub * c.nsub + h * nh;
-      if (gres_w) o_gx = __ldg(gres_x + row);
+      if (gres_w) o_gx = __ldg(gres_x + (long long)b * a.T_out + t);
+      if (has_res) {
+        const float4* p = reinterpret_cast<const float4*>(res + ntc_row(Tp_out, a.res_ld, b, t) + (co >> 2) * 128);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (4 * j < nh) {
-          if (res) o_res[j] = __ldg(reinterpret_cast<const float4*>(res + row * a.res_ld + co) + j);
-          if (has_film) {
-            o_ga[j] = __ldg(reinterpret_cast<const float4*>(a.gamma + row * a.gb_ld + co) + j);
-            o_be[j] = __ldg(reinterpret_cast<const float4*>(a.beta + row * a.gb_ld + co) + j);
+        for (int j = 0; j < 4; ++j)
+          if (NH4 ? j < NH4 : 4 * j < nh) o_res[j] = __ldg(p + 32 * j);
+      }
+      if (has_film) {
+        const long long ro = ntc_row(Tp_out, a.gb_ld, b, t) + (co >> 2) * 128;
+        const float4* pg = reinterpret_cast<const float4*>(a.gamma + ro);
+        const float4* pb = reinterpret_cast<const float4*>(a.beta + ro);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (NH4 ? j < NH4 : 4 * j < nh) {
+            o_ga[j] = __ldg(pg + 32 * j);
+            o_be[j] = __ldg(pb + 32 * j);
           }
-        }
       }
     };
     griddep_wait();  // before the first operand load and the first store
-    load_ops(first, 0);
+    int b = first / c.m_tiles, tile = first - b * c.m_tiles;
+    if (first < n_m) load_ops(b, tile, 0);
     int it = 0;
     for (int m = first; m < n_m; m += step, ++it) {
-      const int b = m / c.m_tiles, t0 = (m - b * c.m_tiles) * kTc2M;
+      // next item of this CTA (no division in the loop)
+      int nb = b + step_b, ntile = tile + step_t;
+      if (ntile >= c.m_tiles) {
+        ntile -= c.m_tiles;
+        ++nb;
+      }
+      const int t0 = tile * kTc2M;
       const uint32_t acc = (uint32_t)it & 1u;
-      const int t = t0 + q * 32 + lane;
+      const int t = t0 + rl;
       const bool ok = t < a.T_out;
-      const long long row = (long long)b * a.T_out + t;
       const int n_rows_seg = min(32, a.T_out - (t0 + q * 32));
-      const int seg = (t0 >> 5) + q;
+      float* raw_row = raw ? raw + ntc_row(Tp_out, a.raw_ld, b, t) : nullptr;
+      float* out_row = out ? out + ntc_row(Tp_out, a.out_ld, b, t) : nullptr;
+      float2* st_row = has_stats ? a.stats + ((long long)b * a.n_seg + (t0 >> 5) + q) * a.C_out : nullptr;
       mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
+      const uint32_t tacc = tmem + acc * acc_stride + lane_addr;
       for (int sub = 0; sub < n_sub; ++sub) {
-        const int nh = min(c.nsub, nvalid - sub * c.nsub) >> 1;  // channels of this thread (multiple of 4, <= 16)
-        const int n4 = nh >> 2;
-        const int col = sub * c.nsub + h * nh;                  // first column inside the N tile
+        const int nh = unit_nh(sub);
+        const int col = sub * c.nsub + h * nh;  // first column inside the N tile
         const int co = co_tile + col;
         float v[16];
-        const uint32_t taddr = tmem + acc * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (j < n4) tmem_ld4_nowait(taddr + 4u * j, v + 4 * j);
+          if (NH4 ? j < NH4 : 4 * j < nh) tmem_ld4_nowait(tacc + (uint32_t)(col + 4 * j), v + 4 * j);
+        const float4* bp = reinterpret_cast<const float4*>(bias + co);
+        float4 b4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (NH4 ? j < NH4 : 4 * j < nh) b4[j] = __ldg(bp + j);
         tmem_ld_wait();
         const float gx = o_gx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (j < n4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co) + j);
-            float x[4] = {v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w};
-            if (res && ok) {
+          if (NH4 ? j < NH4 : 4 * j < nh) {
+            float x[4] = {v[4 * j] + b4[j].x, v[4 * j + 1] + b4[j].y, v[4 * j + 2] + b4[j].z, v[4 * j + 3] + b4[j].w};
+            if (has_res && ok) {
               x[0] += o_res[j].x; x[1] += o_res[j].y; x[2] += o_res[j].z; x[3] += o_res[j].w;
             }
             if (gres_w) {
@@ -449,7 +505,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
               x[0] += fmaf(w4.x, gx, c4.x); x[1] += fmaf(w4.y, gx, c4.y);
               x[2] += fmaf(w4.z, gx, c4.z); x[3] += fmaf(w4.w, gx, c4.w);
             }
-            if (raw && ok) reinterpret_cast<float4*>(raw + row * a.raw_ld + co)[j] = make_float4(x[0], x[1], x[2], x[3]);
+            if (raw_row && ok) reinterpret_cast<float4*>(raw_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
             if (a.post_lrelu) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], x[e] * a.slope);
@@ -462,35 +518,49 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
                 x[0] = x[1] = x[2] = x[3] = 0.f;
               }
             }
-            if (out && ok) reinterpret_cast<float4*>(out + row * a.out_ld + co)[j] = make_float4(x[0], x[1], x[2], x[3]);
+            if (out_row && ok) reinterpret_cast<float4*>(out_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
             v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
           }
         }
         // request the next unit's operands now; they land while this thread waits for the next accumulator
-        if (sub + 1 < n_sub) load_ops(m, sub + 1);
-        else load_ops(m + step, 0);
-        if (a.stats && n_rows_seg > 0) {
+        if (sub + 1 < n_sub) load_ops(b, tile, sub + 1);
+        else if (m + step < n_m) load_ops(nb, ntile, 0);
+        if (has_stats && n_rows_seg > 0) {
           // (mean, M2) of the stored values over this warp's <= 32 rows, per channel: transpose through the
           // warp's smem scratch, then lane (half, ch) sums 16 rows about their first sample; the two halves
           // are merged with Chan's formula.  in_finalize2_kernel merges the segments in double.
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (j < n4)
-              reinterpret_cast<float4*>(scr + lane * c.scr_pitch)[j] =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (NH4 ? j < NH4 : 4 * j < nh)
+              sts128(scr_row + 16u * j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                   __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
           __syncwarp();
           const int hh = lane >> 4, ch = lane & 15;
           const int cnt = max(0, min(16, n_rows_seg - 16 * hh));
           float piv = 0.f, s1 = 0.f, s2 = 0.f;
           if (ch < nh && cnt > 0) {
-            const float* col_p = scr + (16 * hh) * c.scr_pitch + ch;
-            piv = col_p[0];
-#pragma unroll 4
-            for (int i = 1; i < cnt; ++i) {
-              const float dd = col_p[i * c.scr_pitch] - piv;
-              s1 += dd;
-              s2 = fmaf(dd, dd, s2);
+            const uint32_t colp = scr + (uint32_t)((16 * hh) * c.scr_pitch + ch) * 4u;
+            const uint32_t pitch_b = (uint32_t)c.scr_pitch * 4u;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(piv) : "r"(colp));
+            if (cnt == 16) {
+              float xv[15];
+#pragma unroll
+              for (int i = 0; i < 15; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[i]) : "r"(colp + (i + 1) * pitch_b));
+#pragma unroll
+              for (int i = 0; i < 15; ++i) {
+                const float dd = xv[i] - piv;
+                s1 += dd;
+                s2 = fmaf(dd, dd, s2);
+              }
+            } else {
+              for (int i = 1; i < cnt; ++i) {
+                float xi;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xi) : "r"(colp + i * pitch_b));
+                const float dd = xi - piv;
+                s1 += dd;
+                s2 = fmaf(dd, dd, s2);
+              }
             }
           }
           const float n1 = (float)cnt;
@@ -504,12 +574,14 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
             const float dd = mean_o - mean;
             mean += dd * n_o / nn;
             m2 += m2_o + dd * dd * n1 * n_o / nn;
-            a.stats[((long long)b * a.n_seg + seg) * a.C_out + co + ch] = make_float2(mean, m2);
+            st_row[co + ch] = make_float2(mean, m2);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(bars + kBarAccEmpty + acc);
+      b = nb;
+      tile = ntile;
     }
   }
   tc_fence_before();
@@ -520,7 +592,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
   }
 }
 
-// (B, C, T) -> [B][T][C]: the caller's PPG tensor into the channels-last form the bulk-copy producer reads.
+// (B, C, T) -> blocked channels-last: the caller's PPG tensor into the layout the transform role reads.
 __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict__ x, int C, int T, float* __restrict__ y) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
@@ -532,7 +604,7 @@ __global__ void __launch_bounds__(256) nct_to_ntc_kernel(const float* __restrict
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + tx;
-    if (t < T && c < C) y[((long long)b * T + t) * C + c] = tile[tx][i];
+    if (t < T && c < C) y[ntc_row(ntc_tp(T), C, b, t) + ntc_col(c)] = tile[tx][i];
   }
 }
 

@@ -452,8 +452,10 @@ static int tc_setup_kernels() {
   FSVC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(level0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return FSVC_OK;
 }
@@ -599,9 +601,10 @@ static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, si
   const int T = frames * h->hop;
   int T_l = T;
   size_t max_lvl = 0, max_stat = 0, max_bc = 0;
+  // every activation is blocked channels-last (conv_tc2.cuh: ntc_row): utterances are padded to 32-step blocks
   for (int l = 0; l < n; ++l) {
     T_l /= h->dscale[l];
-    const size_t ne = (size_t)B * h->lvl_c[l] * T_l;
+    const size_t ne = (size_t)B * h->lvl_c[l] * ntc_tp(T_l);
     max_lvl = ne > max_lvl ? ne : max_lvl;
     for (int br = 0; br < 2; ++br) ws->y[br][l] = ar.get<float>(ne);
     ws->H[l] = ar.get<float>(2 * ne);
@@ -615,9 +618,9 @@ static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, si
   int T_in = frames;
   for (int i = 0; i < n; ++i) {
     const int C = h->cfg.mid_channels[i], r = h->cfg.upsampling_scales[i];
-    const size_t ne = (size_t)B * C * T_in * r;
+    const size_t ne = (size_t)B * C * ntc_tp(T_in * r);
     ws->e[i] = ar.get<float>((size_t)B * C);
-    ws->h0[i] = ar.get<float>((size_t)B * C * T_in);
+    ws->h0[i] = ar.get<float>((size_t)B * C * ntc_tp(T_in));
     ws->xr[i] = ar.get<float>(ne);
     ws->t1[i] = ar.get<float>(ne);
     ws->x_[i] = ar.get<float>(ne);
@@ -631,8 +634,8 @@ static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, si
   ws->stats = ar.get<float2>(max_stat);
   ws->pa = ar.get<float>(max_bc);
   ws->pc = ar.get<float>(max_bc);
-  ws->xin = ar.get<float>((size_t)B * frames * h->cfg.in_channels);
-  for (int br = 0; br < 2; ++br) ws->ydec[br] = ar.get<float>((size_t)B * T * h->lvl_c[0]);
+  ws->xin = ar.get<float>((size_t)B * ntc_tp(frames) * h->cfg.in_channels);
+  for (int br = 0; br < 2; ++br) ws->ydec[br] = ar.get<float>((size_t)B * ntc_tp(T) * h->lvl_c[0]);
   return ar.off;
 }
 
@@ -724,8 +727,15 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   per_group = per_group < 1 ? 1 : per_group;
   per_group = per_group > items ? items : per_group;
   const dim3 grid(per_group * groups);
-  if (K == 3) launch_pdl(conv_tc3_kernel<3>, grid, kTc3Threads, cfg.total, c.stream, L);
-  else launch_pdl(conv_tc3_kernel<1>, grid, kTc3Threads, cfg.total, c.stream, L);
+  // compile-time epilogue width when every sub-tile of every N tile is a full 24 channels
+  const bool nh3 = cfg.nsub == 24 && p[0].C_out % 24 == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % 24 == 0);
+  if (K == 3) {
+    if (nh3) launch_pdl(conv_tc3_kernel<3, 3>, grid, kTc3Threads, cfg.total, c.stream, L);
+    else launch_pdl(conv_tc3_kernel<3, 0>, grid, kTc3Threads, cfg.total, c.stream, L);
+  } else {
+    if (nh3) launch_pdl(conv_tc3_kernel<1, 3>, grid, kTc3Threads, cfg.total, c.stream, L);
+    else launch_pdl(conv_tc3_kernel<1, 0>, grid, kTc3Threads, cfg.total, c.stream, L);
+  }
   double flops = 0, elems = 0;
   for (int i = 0; i < n_prob; ++i) {
     const Tc2Args& a = p[i];
@@ -871,7 +881,7 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
       launch_tc2(c, h, 3, p, 2, "down_d4");
     }
     for (int br = 0; br < 2; ++br) {
-      p[br] = tc2_args(c, lw.film[br], ws.y[br][l], C, T_l, T_l, 1, ws.H[l] + (size_t)br * C, 2 * C);
+      p[br] = tc2_args(c, lw.film[br], ws.y[br][l], C, T_l, T_l, 1, ws.H[l] + ntc_col(br * C), 2 * C);
       p[br].post_lrelu = 1;
     }
     launch_tc2(c, h, 3, p, 2, "film_conv");
@@ -894,7 +904,7 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
     const int C = h->cfg.mid_channels[i], r = h->cfg.upsampling_scales[i];
     const int l = n - 1 - i, T_s = T_in * r, n_seg = (T_s + 31) / 32;
     const float* gamma = ws.GB[l];
-    const float* beta = ws.GB[l] + C;
+    const float* beta = ws.GB[l] + ntc_col(C);
     const bool norm = spk != nullptr;
     c.label = stage_label[i];
     auto film = [&](Tc2Args& a) {

@@ -337,9 +337,9 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
 #pragma unroll
                   for (int e = 0; e < 8; ++e) v[e] += fmaf(par[kLfR1W * 32 + g * 8 + e], x, par[kLfR1B * 32 + g * 8 + e]);
                   if (p.y_dec[br] && tau >= 0 && tau < kLfValid && t % p.dec == 0) {
-                    float4* yp = reinterpret_cast<float4*>(p.y_dec[br] + ((long long)b * (p.T / p.dec) + t / p.dec) * C + g * 8);
+                    float4* yp = reinterpret_cast<float4*>(p.y_dec[br] + ntc_row(ntc_tp(p.T / p.dec), C, b, t / p.dec) + g * 256);
                     yp[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    yp[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    yp[32] = make_float4(v[4], v[5], v[6], v[7]);
                   }
                 } else {
 #pragma unroll
@@ -373,9 +373,9 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           if (ok) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] += w[e] + s_bout[g * 8 + e];
-            float4* op = reinterpret_cast<float4*>(p.gb + ((long long)b * p.T + t) * (2 * C) + g * 8);
+            float4* op = reinterpret_cast<float4*>(p.gb + ntc_row(ntc_tp(p.T), 2 * C, b, t) + g * 256);
             op[0] = make_float4(v[0], v[1], v[2], v[3]);
-            op[1] = make_float4(v[4], v[5], v[6], v[7]);
+            op[32] = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
       }
