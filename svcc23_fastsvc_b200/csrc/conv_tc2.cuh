@@ -581,51 +581,71 @@ __global__ void __launch_bounds__(kTc2Threads, 2) conv_tc2_kernel(const __grid_c
 
 // ---- small companions -------------------------------------------------------------------
 
-// Merge the per-32-step (mean, M2) partials [B][n_seg][C] of one (b, c) (Chan et al., double,
-// fixed order) and emit the affine the next conv applies on load: a = rstd, c = e - mean*rstd.
+// Merge the per-32-step (mean, M2) partials [B][n_seg][C] of one (b, c) (Chan et al., double, fixed order)
+// and emit the affine the next conv applies on load: a = rstd, c = e - mean*rstd.
 // InstanceNorm2d: biased variance over the whole time axis, eps inside the sqrt (fastsvc.py:76,138).
-// grid = B*C blocks of 64 threads.
-__global__ void __launch_bounds__(64) in_finalize2_kernel(const float2* __restrict__ stats, int n_seg, int T, int C,
-                                                          const float* __restrict__ e, float eps,
-                                                          float* __restrict__ out_a, float* __restrict__ out_c) {
-  const int bc = blockIdx.x, b = bc / C, c = bc - b * C;
-  const int tid = threadIdx.x;
+// One warp per (b, c): lane l merges segments l, l+32, ... (loads issued 8 at a time), then a 5-step
+// butterfly merges the lanes.  grid = ceil(B*C / 8) blocks of 256 threads.
+__device__ __forceinline__ double shfl_xor_d(double v, int o) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, o);
+  hi = __shfl_xor_sync(0xffffffffu, hi, o);
+  return __hiloint2double(hi, lo);
+}
+__global__ void __launch_bounds__(256) in_finalize2_kernel(const float2* __restrict__ stats, int n_seg, int T, int C,
+                                                           int BC, const float* __restrict__ e, float eps,
+                                                           float* __restrict__ out_a, float* __restrict__ out_c) {
+  const int lane = threadIdx.x & 31;
+  const int bc = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (bc >= BC) return;
+  const int b = bc / C, c = bc - b * C;
+  const float2* sp = stats + (long long)b * n_seg * C + c;
   double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int s = tid; s < n_seg; s += 64) {
-    const float2 p = __ldg(stats + ((long long)b * n_seg + s) * C + c);
-    const double nb = (double)min(32, T - s * 32);
-    const double d = (double)p.x - mean, nn = n + nb;
-    mean += d * nb / nn;
-    m2 += (double)p.y + d * d * n * nb / nn;
-    n = nn;
-  }
-  __shared__ double sh[3][64];
-  sh[0][tid] = n;
-  sh[1][tid] = mean;
-  sh[2][tid] = m2;
-  __syncthreads();
-  for (int o = 32; o > 0; o >>= 1) {
-    if (tid < o) {
-      const double n1 = sh[0][tid], n2 = sh[0][tid + o];
-      if (n2 > 0.0) {
-        const double nn = n1 + n2, d = sh[1][tid + o] - sh[1][tid];
-        sh[1][tid] += d * n2 / nn;
-        sh[2][tid] += sh[2][tid + o] + d * d * n1 * n2 / nn;
-        sh[0][tid] = nn;
+  for (int s0 = lane; s0 < n_seg; s0 += 8 * 32) {
+    float2 pv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int sg = s0 + 32 * u;
+      pv[u] = sg < n_seg ? __ldg(sp + (long long)sg * C) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int sg = s0 + 32 * u;
+      if (sg < n_seg) {
+        const double nb = (double)min(32, T - sg * 32);
+        const double d = (double)pv[u].x - mean, nn = n + nb;
+        mean += d * nb / nn;
+        m2 += (double)pv[u].y + d * d * n * nb / nn;
+        n = nn;
       }
     }
-    __syncthreads();
   }
-  if (tid == 0) {
-    const double var = sh[2][0] / (double)T;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double n2 = shfl_xor_d(n, o), mean2 = shfl_xor_d(mean, o), m22 = shfl_xor_d(m2, o);
+    // merge (lower lane's partial, upper lane's partial) in that order on both lanes: bitwise symmetric
+    const bool low = (lane & o) == 0;
+    const double na = low ? n : n2, ma = low ? mean : mean2, qa = low ? m2 : m22;
+    const double nb = low ? n2 : n, mb = low ? mean2 : mean, qb = low ? m22 : m2;
+    const double nn = na + nb;
+    if (nn > 0.0) {
+      const double d = mb - ma;
+      mean = ma + d * nb / nn;
+      m2 = qa + qb + d * d * na * nb / nn;
+    }
+    n = nn;
+  }
+  if (lane == 0) {
+    const double var = m2 / (double)T;
     const double rstd = 1.0 / sqrt(var + (double)eps);
     out_a[bc] = (float)rstd;
-    out_c[bc] = (float)((double)(e ? e[bc] : 0.f) - sh[1][0] * rstd);
+    out_c[bc] = (float)((double)(e ? e[bc] : 0.f) - mean * rstd);
   }
 }
 
 // All stages' speaker projections in one launch: e_i[b][c] = bias_i[c] + W_i[c] . normalize(spk[b])
-// (nn.Linear(F.normalize(spk_emb)), fastsvc.py:135-137).  grid = (B, n_stages), block = 256.
+// (nn.Linear(F.normalize(spk_emb)), fastsvc.py:135-137).  grid = (B, n_stages, ceil(C_max/32)), block = 256:
+// a warp owns 4 output channels and keeps all their loads in flight.
 struct SpkProjArgs {
   const float* W[8];
   const float* bias[8];
@@ -636,6 +656,9 @@ __global__ void __launch_bounds__(256) spk_project_all_kernel(const float* __res
   __shared__ float red[8];
   __shared__ float inv_norm;
   const int b = blockIdx.x, st = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C[st];
+  const int c0 = blockIdx.z * 32 + warp * 4;
+  if (blockIdx.z * 32 >= C) return;
   const float* x = spk + (long long)b * S;
   float ss = 0.f;
   for (int j = tid; j < S; j += 256) ss = fmaf(x[j], x[j], ss);
@@ -649,13 +672,18 @@ __global__ void __launch_bounds__(256) spk_project_all_kernel(const float* __res
   }
   __syncthreads();
   const float inv = inv_norm;
-  const int C = p.C[st];
-  for (int c = warp; c < C; c += 8) {
-    const float* w = p.W[st] + (long long)c * S;
-    float acc = 0.f;
-    for (int j = lane; j < S; j += 32) acc = fmaf(__ldg(w + j), x[j] * inv, acc);
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) p.e[st][(long long)b * C + c] = acc + p.bias[st][c];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = lane; j < S; j += 32) {
+    const float xv = x[j] * inv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (c0 + i < C) acc[i] = fmaf(__ldg(p.W[st] + (long long)(c0 + i) * S + j), xv, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && c0 + i < C) p.e[st][(long long)b * C + c0 + i] = v + p.bias[st][c0 + i];
   }
 }
 

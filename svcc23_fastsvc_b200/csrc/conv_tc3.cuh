@@ -23,10 +23,25 @@
 
 namespace fsvc {
 
-constexpr int kTc3XformWarps = 6;
-constexpr int kTc3XformThreads = 32 * kTc3XformWarps;  // warps 2..9
-constexpr int kTc3EpiThreads = 256;                    // the 8 warps after them
-constexpr int kTc3Threads = 64 + kTc3XformThreads + kTc3EpiThreads;
+// Two CTA shapes of the same kernel:
+//   BIG   (512 threads, one CTA per SM): weights warp, MMA warp, 6 transform warps, 8 epilogue warps -- any conv;
+//   SMALL (224 threads, two CTAs per SM): weights+MMA warp, 2 transform warps, 4 epilogue warps -- convs whose
+//         weights are resident and whose rings fit in half the shared memory (C <= 48): two independent pipelines
+//         per SM double the loads in flight, which is what bounds the long low-channel layers (HBM latency).
+template <bool SMALL>
+struct Tc3Shape {
+  static constexpr int kMmaWarp = SMALL ? 0 : 1;
+  static constexpr int kX0 = SMALL ? 1 : 2;            // first transform warp
+  static constexpr int kXW = SMALL ? 2 : 6;            // transform warps
+  static constexpr int kE0 = kX0 + kXW;                // first epilogue warp
+  static constexpr int kEW = SMALL ? 4 : 8;            // epilogue warps (4 lane quarters x kEH column halves)
+  static constexpr int kEH = kEW / 4;
+  static constexpr int kXT = 32 * kXW, kET = 32 * kEW;
+  static constexpr int kThreads = 32 * (kE0 + kEW);
+  static constexpr int kMinCtas = SMALL ? 2 : 1;
+};
+constexpr int kTc3Threads = Tc3Shape<false>::kThreads;
+constexpr int kTc3ThreadsSmall = Tc3Shape<true>::kThreads;
 constexpr int kTc3ChunkItems = 4;      // 16-byte-chunk items per transform thread and prefetch chunk
 
 struct Tc3Cfg {
@@ -87,22 +102,26 @@ enum {  // mbarrier indices
 };
 
 // Shared-memory plan of one launch.  Returns false when even a 1-deep A ring does not fit.
-__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c) {
+__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool small = false) {
   const int halo = (K / 2) * a.dil, W = kTc2M + 2 * halo;
   const uint32_t Gb = a.CIB / 8;
   c->a_bytes = 2u * Gb * W * 16u;
   c->b_bytes = 2u * K * Gb * a.N_tile * 16u;
   const int nvalid_max = a.C_out < a.N_tile ? a.C_out : a.N_tile;
-  int nsub = 8;
-  for (int cand : {24, 32, 16, 8})
+  // epilogue sub-tile: a thread owns nsub / (column halves) channels, at most 16
+  const int eh = small ? 1 : 2;
+  int nsub = 8 * eh;
+  for (int cand : {12 * eh, 16 * eh, 8 * eh, 4 * eh})
     if (nvalid_max % cand == 0) {
       nsub = cand;
       break;
     }
+  if (small && (!a.w_resident || nvalid_max % nsub != 0)) return false;
   c->nsub = nsub;
-  c->scr_pitch = nsub / 2 <= 12 ? 12 : 20;
+  c->scr_pitch = nsub / eh <= 12 ? 12 : 20;
   const uint32_t w_bytes = a.w_resident ? c->b_bytes * a.n_blk : 0u;
-  const uint32_t scr_bytes = 8u * 32u * c->scr_pitch * 4u;
+  const uint32_t scr_bytes = (small ? 4u : 8u) * 32u * c->scr_pitch * 4u;
+  const uint32_t budget = small ? 113u * 1024u : 227u * 1024u;
   const uint32_t pa_bytes = 3u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;  // triple-buffered per-utterance affine
   for (int slots = 3; slots >= 1; --slots) {
     c->a_slots = slots;
@@ -121,15 +140,19 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c) {
     c->off_bar = off;
     off += kBarCount * 8 + 16;
     c->total = off;
-    if (off <= 227u * 1024u) return true;
+    if (off <= budget) return true;
   }
   return false;
 }
 
 // NH4: float4 units per epilogue thread and sub-tile, fixed at compile time (3 = the 24-channel sub-tile every
 // conv of the YAML generator uses) or 0 = decided at run time (any multiple-of-8 channel count).
-template <int K, int NH4>
-__global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
+// GEN: the A operand is generated from a 1-channel signal (first conv of an unfused level-0 chain).
+template <int K, int NH4, bool SMALL, bool GEN>
+__global__ void __launch_bounds__(Tc3Shape<SMALL>::kThreads, Tc3Shape<SMALL>::kMinCtas)
+conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
+  using SH = Tc3Shape<SMALL>;
+  constexpr int kTc3XformThreads = SH::kXT, kTc3EpiThreads = SH::kET;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw;
   const Tc2Args& a = L.a;
@@ -138,13 +161,18 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
   const int prob = blockIdx.x % c.n_prob;
   const int rest = blockIdx.x / c.n_prob;
   const int nt = rest % a.n_ntiles;
-  const int first = rest / a.n_ntiles;
-  const int step = gridDim.x / (c.n_prob * a.n_ntiles);
-  const int n_m = c.B * c.m_tiles;
+  // items (utterance, 128-step tile) of this CTA: one contiguous range -- neighbouring tiles share their halo rows
+  // in L2 and the utterance (hence the InstanceNorm affine in shared memory) changes at most a few times per CTA
+  const int n_cta = gridDim.x / (c.n_prob * a.n_ntiles);
+  const int cta = rest / a.n_ntiles;
+  const int n_all = c.B * c.m_tiles;
+  const int first = (int)((long long)cta * n_all / n_cta);
+  const int n_m = (int)((long long)(cta + 1) * n_all / n_cta);
+  constexpr int step = 1;
 
   const int halo = (K / 2) * a.dil;
   const int W = kTc2M + 2 * halo;
-  const bool gen = a.gen_w != nullptr;
+  constexpr bool gen = GEN;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + c.off_bar);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kBarCount);
@@ -166,7 +194,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
     mbar_init(bars + kBarWFull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(s_tmem, 2 * acc_stride);
+  if (warp == SH::kMmaWarp) tmem_alloc(s_tmem, 2 * acc_stride);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -176,9 +204,9 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
   const int n_sub = (nvalid + c.nsub - 1) / c.nsub;           // epilogue sub-tiles of this N tile
   const int co_tile = nt * a.N_tile;
 
-  if (warp == 0) {
+  if (warp == 0 && lane == 0) {
     // =============================== WEIGHTS ===============================
-    if (lane == 0) {
+    {
       const uint8_t* w_nt =
           reinterpret_cast<const uint8_t*>(a.w + prob * L.d_w) + (size_t)nt * a.n_blk * c.b_bytes;
       if (a.w_resident) {
@@ -201,13 +229,15 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  }
+  if (warp == SH::kMmaWarp) {
     // =============================== MMA ISSUER ===============================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(kTc2M, a.N_tile);
       const uint32_t Gb = (uint32_t)a.CIB >> 3;
       const uint32_t strip = (uint32_t)W * 16u, a_plane = Gb * strip;
       const uint32_t b_strip = (uint32_t)a.N_tile * 16u, b_half = (uint32_t)K * Gb * b_strip;
+      const uint32_t a_hiw = (uint32_t)(umma_desc(0, strip, 128) >> 32), b_hiw = (uint32_t)(umma_desc(0, b_strip, 128) >> 32);
       if (a.w_resident) mbar_wait2(bars + kBarWFull, 0);
       uint32_t pa_pos = 0, pbk = 0;
       int it = 0;
@@ -228,19 +258,19 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
           }
           tc_fence_after();
           const uint32_t sA_addr = smem_u32(smem + c.off_a + aslot * c.a_bytes);
-#pragma unroll
+          // descriptors differ only in the 14-bit start-address field of the low word (addresses < 256 KB)
+          const uint32_t a_w0 = (uint32_t)umma_desc(sA_addr, strip, 128), b_w0 = (uint32_t)umma_desc(sB_addr, b_strip, 128);
           for (int k = 0; k < K; ++k) {
+            uint32_t a_w = a_w0 + (uint32_t)(k * a.dil), b_w = b_w0 + (((uint32_t)k * Gb * b_strip) >> 4);
             for (uint32_t kc = 0; kc < (uint32_t)a.CIB / 16u; ++kc) {
-              const uint32_t a_off = 2u * kc * strip + (uint32_t)(k * a.dil) * 16u;
-              const uint32_t b_off = ((uint32_t)k * Gb + 2u * kc) * b_strip;
-              const uint64_t a_hi = umma_desc(sA_addr + a_off, strip, 128);
-              const uint64_t a_lo = umma_desc(sA_addr + a_plane + a_off, strip, 128);
-              const uint64_t b_hi = umma_desc(sB_addr + b_off, b_strip, 128);
-              const uint64_t b_lo = umma_desc(sB_addr + b_half + b_off, b_strip, 128);
+              const uint64_t a_hi = ((uint64_t)a_hiw << 32) | a_w, a_lo = ((uint64_t)a_hiw << 32) | (a_w + (a_plane >> 4));
+              const uint64_t b_hi = ((uint64_t)b_hiw << 32) | b_w, b_lo = ((uint64_t)b_hiw << 32) | (b_w + (b_half >> 4));
               const uint32_t accum = (blk == 0 && k == 0 && kc == 0) ? 0u : 1u;
               umma_bf16(d_tmem, a_lo, b_hi, idesc, accum);  // small terms first, then the dominant one
               umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
               umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+              a_w += (2u * strip) >> 4;
+              b_w += (2u * b_strip) >> 4;
             }
           }
           umma_commit(bars + kBarAEmpty + aslot);
@@ -253,9 +283,9 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         }
       }
     }
-  } else if (warp < 2 + kTc3XformWarps) {
+  } else if (warp >= SH::kX0 && warp < SH::kE0) {
     // =============================== TRANSFORM ===============================
-    const int tt = tid - 64;
+    const int tt = tid - 32 * SH::kX0;
     const uint32_t smem_base = smem_u32(smem);
     const float* in = a.in + prob * L.d_in;  // gen mode: 1-channel signal [B][T_in]
     const float* gen_w = gen ? a.gen_w + prob * L.d_gen_w : nullptr;
@@ -291,6 +321,11 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
         }
       }
     };
+    // Affine buffers are indexed by the number of utterance changes so far (three buffers: a rewrite follows the
+    // named barrier of the previous change, which every thread passes only after converting the tiles before it).
+    int pa_b = -1;
+    uint32_t pa_epoch = 0, cv_epoch = 0;  // epoch of the tile being loaded / converted
+    int cv_b = -1;
     // issue the loads of one chunk (no use of the results)
     auto load_chunk = [&](const Cursor& q, float4 (&d)[CH][2], uint32_t& live) {
       live = 0;
@@ -299,8 +334,10 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
       const int ci0 = q.blk * a.CIB;
       // InstanceNorm affine of this tile's utterance, written one chunk early.  Three buffers: the write for
       // tile i+3 follows the named barrier of tile i+1, which every thread reaches only after converting tile i.
-      if (q.blk == 0 && q.ch == 0 && a.pre_a) {
-        float* s_pa = s_pa_base + (q.it % 3) * 2 * cpad;
+      if (q.blk == 0 && q.ch == 0 && a.pre_a && b != pa_b) {
+        pa_b = b;
+        ++pa_epoch;
+        float* s_pa = s_pa_base + (pa_epoch % 3) * 2 * cpad;
         for (int ch = tt; ch < cpad; ch += kTc3XformThreads) {
           s_pa[ch] = ch < a.C_in ? __ldg(a.pre_a + (long long)b * a.C_in + ch) : 1.f;
           s_pa[cpad + ch] = ch < a.C_in ? __ldg(a.pre_c + (long long)b * a.C_in + ch) : 0.f;
@@ -335,10 +372,14 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
       const uint32_t aslot = pa_pos % (uint32_t)c.a_slots, ause = pa_pos / (uint32_t)c.a_slots;
       if (q.ch == 0) {
         if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
-        if (q.blk == 0 && a.pre_a) named_bar_sync(1, kTc3XformThreads);  // s_pa of this tile is complete
+        if (q.blk == 0 && a.pre_a && q.b != cv_b) {  // new utterance: its affine was written one chunk ago
+          cv_b = q.b;
+          ++cv_epoch;
+          named_bar_sync(1, kTc3XformThreads);
+        }
       }
       const uint32_t sA = smem_base + c.off_a + aslot * c.a_bytes;
-      const uint32_t s_pa = smem_base + c.off_pa + (uint32_t)((q.it % 3) * 2 * cpad) * 4u;
+      const uint32_t s_pa = smem_base + c.off_pa + (uint32_t)((cv_epoch % 3) * 2 * cpad) * 4u;
       const uint32_t s_pc = s_pa + (uint32_t)cpad * 4u;
       const int ci0 = q.blk * a.CIB;
 #pragma unroll
@@ -391,24 +432,25 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
     };
     // software pipeline over the chunk sequence: chunk k+1 is in flight while chunk k is converted
     Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
-    float4 d0[CH][2], d1[CH][2];
-    uint32_t live0, live1;
-    load_chunk(cur, d0, live0);
+    float4 dc[CH][2], dn[CH][2];
+    uint32_t live_c, live_n;
+    load_chunk(cur, dc, live_c);
     while (cur.m < n_m) {
       Cursor nxt = cur;
       advance(nxt);
-      load_chunk(nxt, d1, live1);
-      convert_chunk(cur, d0, live0);
-      if (nxt.m >= n_m) break;
-      cur = nxt;
-      advance(nxt);
-      load_chunk(nxt, d0, live0);
-      convert_chunk(cur, d1, live1);
+      load_chunk(nxt, dn, live_n);
+      convert_chunk(cur, dc, live_c);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        dc[j][0] = dn[j][0];
+        dc[j][1] = dn[j][1];
+      }
+      live_c = live_n;
       cur = nxt;
     }
-  } else {
+  } else if (warp >= SH::kE0) {
     // =============================== EPILOGUE ===============================
-    const int ew = warp - (2 + kTc3XformWarps);
+    const int ew = warp - SH::kE0;
     const int q = warp & 3, h = ew >> 2;
     const float* bias = a.bias + prob * L.d_bias;
     const float* res = a.res ? a.res + prob * L.d_res : nullptr;
@@ -426,7 +468,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
     const long long Tp_out = ntc_tp(a.T_out);
 
     // channels of this thread in sub-tile `sub`: nh (multiple of 4), starting at column sub*nsub + h*nh
-    auto unit_nh = [&](int sub) { return NH4 ? 4 * NH4 : (min(c.nsub, nvalid - sub * c.nsub) >> 1); };
+    auto unit_nh = [&](int sub) { return NH4 ? 4 * NH4 : (min(c.nsub, nvalid - sub * c.nsub) / SH::kEH); };
 
     // operands of one (tile, sub-tile) unit for this thread: requested one unit ahead of their use
     float4 o_res[4], o_ga[4], o_be[4];
@@ -586,7 +628,7 @@ __global__ void __launch_bounds__(kTc3Threads, 1) conv_tc3_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == SH::kMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem, 2 * acc_stride);
   }

@@ -452,10 +452,15 @@ static int tc_setup_kernels() {
   FSVC_CUDA(cudaFuncSetAttribute(conv1d_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+#define FSVC_ATTR(K_, NH_, SM_)                                                                                         \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                 max_smem));                                                                            \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+  FSVC_ATTR(3, 3, false);
+  FSVC_ATTR(3, 0, false);
+  FSVC_ATTR(1, 3, false);
+  FSVC_ATTR(1, 0, false);
+#undef FSVC_ATTR
   FSVC_CUDA(cudaFuncSetAttribute(level0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return FSVC_OK;
 }
@@ -717,25 +722,35 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   cfg.n_prob = n_prob;
   cfg.B = c.B;
   cfg.m_tiles = (p[0].T_out + kTc2M - 1) / kTc2M;
-  if (!tc3_plan_smem(p[0], K, &cfg)) {
+  const int groups = n_prob * p[0].n_ntiles;
+  const int items = c.B * cfg.m_tiles;
+  // two half-size CTAs per SM when the conv allows it and there is enough work to keep both pipelines busy
+  // (measured: two 224-thread CTAs per SM are no faster than one 512-thread CTA on any layer -- kept as a template
+  //  option of the kernel, not instantiated)
+  const bool small = false;
+  if (!small && !tc3_plan_smem(p[0], K, &cfg, false)) {
     c.err = 1;
     return;
   }
-  const int groups = n_prob * p[0].n_ntiles;
-  const int items = c.B * cfg.m_tiles;
-  int per_group = h->num_sms / groups;
+  int per_group = (small ? 2 : 1) * h->num_sms / groups;
   per_group = per_group < 1 ? 1 : per_group;
   per_group = per_group > items ? items : per_group;
   const dim3 grid(per_group * groups);
-  // compile-time epilogue width when every sub-tile of every N tile is a full 24 channels
-  const bool nh3 = cfg.nsub == 24 && p[0].C_out % 24 == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % 24 == 0);
+  // compile-time epilogue width (12 channels per thread) when every sub-tile of every N tile is full
+  const int per_thread = cfg.nsub / (small ? 1 : 2);
+  const bool nh3 = per_thread == 12 && p[0].C_out % cfg.nsub == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % cfg.nsub == 0);
+  const int threads = small ? kTc3ThreadsSmall : kTc3Threads;
+#define FSVC_TC3(K_, NH_, SM_)                                                                              \
+  do {                                                                                                     \
+    if (p[0].gen_w) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, true>, grid, threads, cfg.total, c.stream, L); \
+    else launch_pdl(conv_tc3_kernel<K_, NH_, SM_, false>, grid, threads, cfg.total, c.stream, L);           \
+  } while (0)
   if (K == 3) {
-    if (nh3) launch_pdl(conv_tc3_kernel<3, 3>, grid, kTc3Threads, cfg.total, c.stream, L);
-    else launch_pdl(conv_tc3_kernel<3, 0>, grid, kTc3Threads, cfg.total, c.stream, L);
+    if (nh3) FSVC_TC3(3, 3, false); else FSVC_TC3(3, 0, false);
   } else {
-    if (nh3) launch_pdl(conv_tc3_kernel<1, 3>, grid, kTc3Threads, cfg.total, c.stream, L);
-    else launch_pdl(conv_tc3_kernel<1, 0>, grid, kTc3Threads, cfg.total, c.stream, L);
+    if (nh3) FSVC_TC3(1, 3, false); else FSVC_TC3(1, 0, false);
   }
+#undef FSVC_TC3
   double flops = 0, elems = 0;
   for (int i = 0; i < n_prob; ++i) {
     const Tc2Args& a = p[i];
@@ -774,7 +789,9 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
       sp.e[i] = ws.e[i];
       sp.C[i] = h->cfg.mid_channels[i];
     }
-    spk_project_all_kernel<<<dim3(B, n), 256, 0, stream>>>(spk, S, sp);
+    int c_max = 0;
+    for (int i = 0; i < n; ++i) c_max = sp.C[i] > c_max ? sp.C[i] : c_max;
+    spk_project_all_kernel<<<dim3(B, n, (c_max + 31) / 32), 256, 0, stream>>>(spk, S, sp);
     c.label = "";
     c.launched("spk_project", 0.0, 0.0);
   }
@@ -918,7 +935,8 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
     };
     auto finalize = [&]() {
       if (!norm) return;
-      in_finalize2_kernel<<<B * C, 64, 0, stream>>>(ws.stats, n_seg, T_s, C, ws.e[i], c.eps, ws.pa, ws.pc);
+      in_finalize2_kernel<<<(B * C + 7) / 8, 256, 0, stream>>>(ws.stats, n_seg, T_s, C, B * C, ws.e[i], c.eps, ws.pa,
+                                                               ws.pc);
       c.launched("in_finalize", 0.0, 8.0 * B * C * n_seg);
     };
     auto pre = [&](Tc2Args& a) {
