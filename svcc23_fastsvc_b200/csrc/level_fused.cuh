@@ -86,7 +86,7 @@ struct LevelFusedArgs {
 };
 
 struct LevelFusedSmem {
-  uint32_t off_w_c2[2], off_w_c4[2], off_w_film[2], off_w_out, off_buf[4], off_zero, off_sig, off_par, off_bar, total;
+  uint32_t off_w_c2[2], off_w_c4[2], off_w_film[2], off_w_out, off_buf[4], off_zero, off_sig, off_par, off_desc, off_bar, total;
   uint32_t w1_bytes, w2_bytes, buf_bytes;
 };
 __host__ __device__ inline LevelFusedSmem level_fused_smem(int C, int Gp, int N1, int N2) {
@@ -106,6 +106,8 @@ __host__ __device__ inline LevelFusedSmem level_fused_smem(int C, int Gp, int N1
   s.off_zero = off; off += kLfRows * 16u;  // the shared K-padding strip (must lie above every buffer)
   s.off_sig = off; off += 2u * kLfRows * 4u;
   s.off_par = off; off += (2u * 9u * 32u + 64u) * 4u;
+  off = (off + 15u) & ~15u;
+  s.off_desc = off; off += (6u * 2u * 3u * (Gp / 2) + 2u * 3u * (G2 / 2)) * 24u;  // precomputed UMMA descriptors
   off = (off + 15u) & ~15u;
   s.off_bar = off; off += 8 * 8 + 16;
   s.total = off;
@@ -165,6 +167,53 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
     }
     s_par[i] = v;
   }
+  // ---- UMMA descriptor table.  Every (layer, branch, M-tile, tap, K chunk) uses the same shared-memory
+  //      addresses for every work item, so the three descriptors of a chunk (a_hi, a_lo, [w_hi|w_lo]) are built
+  //      once, in issue order; the MMA thread then only streams them (its instruction rate is what bounds the
+  //      kernel otherwise: ~40 instructions of address arithmetic per chunk against a 16-cycle MMA).
+  {
+    uint2* s_desc = reinterpret_cast<uint2*>(smem + L.off_desc);
+    const uint32_t n1 = 3u * (uint32_t)(Gp / 2), G2 = 2u * (uint32_t)G, n2 = 3u * (G2 / 2);
+    const uint32_t n_chain = 6u * 2u * n1, n_all = n_chain + 2u * n2;
+    const uint32_t buf0 = smem_u32(smem + buf_off0), zero_addr = smem_u32(smem + L.off_zero), w_base = smem_u32(smem);
+    const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
+    auto desc_lo = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
+    for (uint32_t e = tid; e < n_all; e += kLfThreads) {
+      uint32_t a0, a1h, a1l, b_addr, b_grp;
+      if (e < n_chain) {
+        const uint32_t lb = e / (2u * n1), r = e - lb * 2u * n1;
+        const int layer = (int)(lb >> 1), br = (int)(lb & 1u);
+        const int mt = (int)(r / n1), kk = (int)(r - (uint32_t)mt * n1);
+        const int k = kk / (Gp / 2), kc = kk - k * (Gp / 2);
+        const int s0 = layer == 0 ? -6 : (layer == 1 ? -2 : -1), d = layer == 0 ? 2 : (layer == 1 ? 4 : 1);
+        const int src = layer == 1 ? 1 : 0;  // a1 / y live in X (0), a2 in Y (1)
+        const uint32_t w_addr = w_base + (layer == 0 ? L.off_w_c2[br] : (layer == 1 ? L.off_w_c4[br] : L.off_w_film[br]));
+        const uint32_t rbytes = (uint32_t)(s0 + kLfHalo - d + k * d + 128 * mt) * 16u;
+        const int g0 = 2 * kc, g1 = g0 + 1;
+        a0 = buf0 + (uint32_t)(2 * br + src) * buf_bytes + (uint32_t)g0 * strip + rbytes;
+        // second 8-channel column: the next real group, or the shared zero strip for the K padding
+        a1h = g1 < G ? a0 + strip : zero_addr + rbytes;
+        a1l = g1 < G ? a0 + plane + strip : zero_addr + rbytes;
+        b_grp = 2u * (uint32_t)p.N1 * 16u;
+        b_addr = w_addr + ((uint32_t)k * Gp + g0) * b_grp;
+      } else {
+        const uint32_t r = e - n_chain;
+        const int mt = (int)(r / n2), kk = (int)(r - (uint32_t)mt * n2);
+        const int k = kk / (int)(G2 / 2);
+        const uint32_t kc = (uint32_t)kk - (uint32_t)k * (G2 / 2);
+        const uint32_t rbytes = (uint32_t)(kLfHalo + (k - 1) + 128 * mt) * 16u;
+        const uint32_t v0 = 2u * kc, v1 = v0 + 1;  // virtual channel groups of [h_lft (Y_0) | h_sine (Y_1)]
+        a0 = buf0 + (v0 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v0 % G) * strip + rbytes;
+        a1h = buf0 + (v1 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v1 % G) * strip + rbytes;
+        a1l = a1h + plane;
+        b_grp = 2u * (uint32_t)p.N2 * 16u;
+        b_addr = w_base + L.off_w_out + ((uint32_t)k * G2 + v0) * b_grp;
+      }
+      s_desc[3 * e + 0] = make_uint2(desc_lo(a0, a1h - a0), desc_hi);                    // a_hi
+      s_desc[3 * e + 1] = make_uint2(desc_lo(a0 + plane, a1l - (a0 + plane)), desc_hi);  // a_lo
+      s_desc[3 * e + 2] = make_uint2(desc_lo(b_addr, b_grp), desc_hi);                   // [w_hi | w_lo]
+    }
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -186,81 +235,50 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
       mbar_wait2(bar_w, 0);
       const uint32_t idesc_c = umma_idesc_bf16(128, 2 * p.N1), idesc_h = umma_idesc_bf16(128, p.N1);
       const uint32_t idesc_oc = umma_idesc_bf16(128, 2 * p.N2), idesc_oh = umma_idesc_bf16(128, p.N2);
-      const uint32_t buf0 = smem_u32(smem + buf_off0), zero_addr = smem_u32(smem + L.off_zero);
-      const uint32_t w_base = smem_u32(smem);
+      const uint32_t desc_base = smem_u32(smem + L.off_desc);
+      const uint32_t n1 = 3u * (uint32_t)(Gp / 2), n2 = 3u * (uint32_t)G;
       uint32_t ready_phase0 = 0u, ready_phase1 = 0u;
-      auto mk = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
-      // Descriptor words: bits [0,14) of the low word = start address >> 4, bits [16,30) = leading-dimension
-      // byte offset >> 4 (distance between the two 8-channel columns of a K=16 slice); high word = SBO | version.
-      auto desc_lo = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
-      const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
-      // one C->C layer of branch br: A = buffer `src` (0 = X, 1 = Y), window start s, dilation d
-      auto issue_layer = [&](int br, int src, uint32_t w_addr, int s, int d) {
-        const uint32_t row0 = (uint32_t)(s + kLfHalo - d);
-        const uint32_t a_base = buf0 + (uint32_t)(2 * br + src) * buf_bytes;
-        const uint32_t b_grp = 2u * (uint32_t)p.N1 * 16u;  // one ci group of B: hi rows | lo rows
-        if (br == 0) {
-          mbar_wait2(bar_ready, ready_phase0);
-          ready_phase0 ^= 1u;
-        } else {
-          mbar_wait2(bar_ready + 1, ready_phase1);
-          ready_phase1 ^= 1u;
-        }
-        tc_fence_after();
-        for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t d_tmem = tmem + (uint32_t)(2 * br + mt) * 64u;
-          uint32_t accum = 0u;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const uint32_t rbytes = (row0 + (uint32_t)(k * d + 128 * mt)) * 16u;
-            for (int kc = 0; kc < Gp / 2; ++kc) {
-              const int g0 = 2 * kc, g1 = g0 + 1;
-              const uint32_t a0 = a_base + (uint32_t)g0 * strip + rbytes;
-              // second 8-channel column: the next real group, or the shared zero strip for the K padding
-              const uint32_t a1h = g1 < G ? a0 + strip : zero_addr + rbytes;
-              const uint32_t a1l = g1 < G ? a0 + plane + strip : zero_addr + rbytes;
-              const uint32_t b_addr = w_addr + ((uint32_t)k * Gp + g0) * b_grp;
-              const uint64_t A_hi = mk(desc_lo(a0, a1h - a0), desc_hi);
-              const uint64_t A_lo = mk(desc_lo(a0 + plane, a1l - (a0 + plane)), desc_hi);
-              const uint64_t Bd = mk(desc_lo(b_addr, b_grp), desc_hi);
-              umma_bf16(d_tmem, A_hi, Bd, idesc_c, accum);  // a_hi x [w_hi | w_lo]  -> columns [0, 2N)
-              umma_bf16(d_tmem, A_lo, Bd, idesc_h, 1u);     // a_lo x w_hi           -> columns [0, N)
-              accum = 1u;
-            }
-          }
-          umma_commit(bar_acc + 2 * br + mt);
+      auto lds64 = [](uint32_t addr) {
+        uint64_t v;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+        return v;
+      };
+      // stream the precomputed descriptors of one M-tile: a_hi x [w_hi | w_lo] -> columns [0, 2N), a_lo x w_hi -> [0, N)
+      auto issue_mtile = [&](uint32_t d_tmem, uint32_t& dp, uint32_t n_chunks, uint32_t idesc_wide, uint32_t idesc_half) {
+        uint32_t accum = 0u;
+        for (uint32_t i = 0; i < n_chunks; ++i, dp += 24u) {
+          const uint64_t A_hi = lds64(dp), A_lo = lds64(dp + 8u), Bd = lds64(dp + 16u);
+          umma_bf16(d_tmem, A_hi, Bd, idesc_wide, accum);
+          umma_bf16(d_tmem, A_lo, Bd, idesc_half, 1u);
+          accum = 1u;
         }
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        for (int br = 0; br < 2; ++br) issue_layer(br, 0, w_base + L.off_w_c2[br], -6, 2);    // a1 (X) -> a2 (Y)
-        for (int br = 0; br < 2; ++br) issue_layer(br, 1, w_base + L.off_w_c4[br], -2, 4);    // a2 (Y) -> y  (X)
-        for (int br = 0; br < 2; ++br) issue_layer(br, 0, w_base + L.off_w_film[br], -1, 1);  // y  (X) -> h  (Y)
+        uint32_t dp = desc_base;
+        for (int layer = 0; layer < 3; ++layer) {      // a1 (X) -> a2 (Y) -> y (X) -> h (Y), branches interleaved
+          for (int br = 0; br < 2; ++br) {
+            if (br == 0) {
+              mbar_wait2(bar_ready, ready_phase0);
+              ready_phase0 ^= 1u;
+            } else {
+              mbar_wait2(bar_ready + 1, ready_phase1);
+              ready_phase1 ^= 1u;
+            }
+            tc_fence_after();
+            for (int mt = 0; mt < 2; ++mt) {
+              issue_mtile(tmem + (uint32_t)(2 * br + mt) * 64u, dp, n1, idesc_c, idesc_h);
+              umma_commit(bar_acc + 2 * br + mt);
+            }
+          }
+        }
         // merged film_out over the virtual channel concat [h_lft (Y_0) | h_sine (Y_1)]
         mbar_wait2(bar_ready, ready_phase0);
         ready_phase0 ^= 1u;
         mbar_wait2(bar_ready + 1, ready_phase1);
         ready_phase1 ^= 1u;
         tc_fence_after();
-        const uint32_t G2 = 2u * G, b_grp = 2u * (uint32_t)p.N2 * 16u;
-        const uint32_t w_addr = w_base + L.off_w_out;
         for (int mt = 0; mt < 2; ++mt) {
-          const uint32_t d_tmem = tmem + (uint32_t)mt * 128u;
-          uint32_t accum = 0u;
-          for (int k = 0; k < 3; ++k) {
-            const uint32_t rbytes = (uint32_t)(kLfHalo + (k - 1) + 128 * mt) * 16u;
-            for (uint32_t kc = 0; kc < G2 / 2; ++kc) {
-              const uint32_t v0 = 2u * kc, v1 = v0 + 1;
-              const uint32_t a0 = buf0 + (v0 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v0 % G) * strip + rbytes;
-              const uint32_t a1 = buf0 + (v1 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v1 % G) * strip + rbytes;
-              const uint32_t b_addr = w_addr + ((uint32_t)k * G2 + v0) * b_grp;
-              const uint64_t A_hi = mk(desc_lo(a0, a1 - a0), desc_hi);
-              const uint64_t A_lo = mk(desc_lo(a0 + plane, a1 - a0), desc_hi);
-              const uint64_t Bd = mk(desc_lo(b_addr, b_grp), desc_hi);
-              umma_bf16(d_tmem, A_hi, Bd, idesc_oc, accum);
-              umma_bf16(d_tmem, A_lo, Bd, idesc_oh, 1u);
-              accum = 1u;
-            }
-          }
+          issue_mtile(tmem + (uint32_t)mt * 128u, dp, n2, idesc_oc, idesc_oh);
           umma_commit(bar_acc + mt);
         }
       }
