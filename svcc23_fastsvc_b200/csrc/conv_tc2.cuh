@@ -40,6 +40,12 @@ struct Tc2Args {
   int up, down;        // source row of output-rate index u: (u / up) * down
   const float* pre_a;  // [B][C_in] InstanceNorm affine applied on load (or nullptr)
   const float* pre_c;
+  // Alternative to pre_a/pre_c (conv_tc3 only): the producer's per-segment (mean, M2) partials [B][pre_nseg][C_in]
+  // are merged by the consumer itself (no separate finalize launch): a = rstd, c = pre_e - mean * rstd.
+  const float2* pre_stats;
+  const float* pre_e;  // [B][C_in] projected speaker embedding, or nullptr
+  int pre_nseg;        // 32-step segments per utterance (the last may be short: T_in rows in total)
+  float pre_eps;
   int pre_lrelu;
   const float* gen_w;  // != nullptr: `in` is a 1-channel signal [B][T_in] and the C_in operand channels are
   const float* gen_b;  //   gen_b[c] + sum_k gen_w[k*C_in+c] * lrelu(x[u+k-1])   (first conv of a level-0 chain)

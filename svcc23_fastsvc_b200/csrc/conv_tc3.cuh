@@ -51,7 +51,7 @@ struct Tc3Cfg {
   int a_slots;    // depth of the A ring (1..3)
   int scr_pitch;  // floats per row of the per-warp statistics scratch (12 or 20)
   uint32_t a_bytes, b_bytes;  // per ring slot
-  uint32_t off_w, off_a, off_b, off_scr, off_pa, off_bar, total;
+  uint32_t off_w, off_a, off_b, off_scr, off_pa, off_fin, off_tab, off_bar, total;
 };
 
 struct Tc3Launch {
@@ -75,6 +75,23 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ int4 lds128i(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// two predicated 128-bit read-only loads 512 bytes apart (the two 4-channel halves of an 8-channel group)
+__device__ __forceinline__ void ldg2_pred(const float4* p, uint32_t ok, float4& x, float4& y) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pp;\n"
+      "setp.ne.u32 pp, %9, 0;\n"
+      "@pp ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%8];\n"
+      "@pp ld.global.nc.v4.f32 {%4,%5,%6,%7}, [%8+512];\n"
+      "}"
+      : "+f"(x.x), "+f"(x.y), "+f"(x.z), "+f"(x.w), "+f"(y.x), "+f"(y.y), "+f"(y.z), "+f"(y.w)
+      : "l"(p), "r"(ok));
+}
 // bf16 hi|lo split of 8 fp32 values, stored as two 16-byte chunks (32-bit shared-space addresses)
 __device__ __forceinline__ void split_store_s(uint32_t addr, uint32_t plane, const float (&v)[8]) {
   uint32_t hi[4], lo[4];
@@ -88,6 +105,49 @@ __device__ __forceinline__ void split_store_s(uint32_t addr, uint32_t plane, con
   }
   sts128(addr, make_uint4(hi[0], hi[1], hi[2], hi[3]));
   sts128(addr + plane, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+}
+
+// bf16 hi|lo split of 8 fp32 values into two packed 16-byte chunks
+__device__ __forceinline__ void split_bf16(const float (&v)[8], uint4& hi, uint4& lo) {
+  uint32_t h4[4], l4[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+    h4[e] = *reinterpret_cast<const uint32_t*>(&h);
+    l4[e] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  hi = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+  lo = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+}
+// same split, stored under predicates: value where (pv & 1), zeros where (pz & 1), nothing otherwise
+__device__ __forceinline__ void split_store_p(uint32_t addr, uint32_t plane, const float (&v)[8], uint32_t pv, uint32_t pz) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  asm volatile(
+      "{\n"
+      ".reg .pred pv, pz;\n"
+      ".reg .b32 zz;\n"
+      "and.b32 zz, %10, 1;\n"
+      "setp.ne.u32 pv, zz, 0;\n"
+      "and.b32 zz, %11, 1;\n"
+      "setp.ne.u32 pz, zz, 0;\n"
+      "mov.b32 zz, 0;\n"
+      "@pv st.shared.v4.b32 [%0], {%2,%3,%4,%5};\n"
+      "@pv st.shared.v4.b32 [%1], {%6,%7,%8,%9};\n"
+      "@pz st.shared.v4.b32 [%0], {zz,zz,zz,zz};\n"
+      "@pz st.shared.v4.b32 [%1], {zz,zz,zz,zz};\n"
+      "}" ::"r"(addr), "r"(addr + plane), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(lo[0]), "r"(lo[1]),
+      "r"(lo[2]), "r"(lo[3]), "r"(pv), "r"(pz)
+      : "memory");
 }
 
 enum {  // mbarrier indices
@@ -120,7 +180,7 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
   c->nsub = nsub;
   c->scr_pitch = nsub / eh <= 12 ? 12 : 20;
   const uint32_t w_bytes = a.w_resident ? c->b_bytes * a.n_blk : 0u;
-  const uint32_t scr_bytes = (small ? 4u : 8u) * 32u * c->scr_pitch * 4u;
+  const uint32_t scr_bytes = (small ? 4u : 8u) * (32u * c->scr_pitch + 16u) * 4u;
   const uint32_t budget = small ? 113u * 1024u : 227u * 1024u;
   const uint32_t pa_bytes = 3u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;  // triple-buffered per-utterance affine
   for (int slots = 3; slots >= 1; --slots) {
@@ -137,6 +197,10 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
     c->off_pa = off;
     off += pa_bytes;
     off = (off + 15u) & ~15u;
+    c->off_fin = off;
+    off += a.pre_stats ? (uint32_t)(small ? 64 : 192) * 32u : 0u;  // statistics merge scratch: 4 doubles per thread
+    c->off_tab = off;
+    off += Gb * (uint32_t)((W + 31) / 32) * 16u;  // transform geometry table
     c->off_bar = off;
     off += kBarCount * 8 + 16;
     c->total = off;
@@ -148,7 +212,9 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
 // NH4: float4 units per epilogue thread and sub-tile, fixed at compile time (3 = the 24-channel sub-tile every
 // conv of the YAML generator uses) or 0 = decided at run time (any multiple-of-8 channel count).
 // GEN: the A operand is generated from a 1-channel signal (first conv of an unfused level-0 chain).
-template <int K, int NH4, bool SMALL, bool GEN>
+// MODE: 0 = table-driven transform (source row = window row * down), 1 = GEN, 2 = nearest-repeat input (up > 1,
+// down == 1): every source row is converted once and stored to its `up` window rows.
+template <int K, int NH4, bool SMALL, int MODE>
 __global__ void __launch_bounds__(Tc3Shape<SMALL>::kThreads, Tc3Shape<SMALL>::kMinCtas)
 conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   using SH = Tc3Shape<SMALL>;
@@ -172,6 +238,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
 
   const int halo = (K / 2) * a.dil;
   const int W = kTc2M + 2 * halo;
+  constexpr bool GEN = MODE == 1;
   constexpr bool gen = GEN;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + c.off_bar);
@@ -284,6 +351,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       }
     }
   } else if (warp >= SH::kX0 && warp < SH::kE0) {
+   if constexpr (GEN) {
     // =============================== TRANSFORM ===============================
     const int tt = tid - 32 * SH::kX0;
     const uint32_t smem_base = smem_u32(smem);
@@ -448,6 +516,377 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       live_c = live_n;
       cur = nxt;
     }
+   } else {
+    // =============================== TRANSFORM (warp tasks) ===============================
+    // A warp task = (8-channel group g, 32-row segment of the A window): lane <-> row, so g and every address term
+    // but the lane are warp-uniform, all global / shared accesses are 512 contiguous bytes per warp instruction, and
+    // the body is branch-free (rows outside the utterance are stored as zeros by a predicated store) so the up to
+    // four tasks of a chunk interleave in the instruction stream.
+    const int tt = tid - 32 * SH::kX0, xw = warp - SH::kX0;
+    const uint32_t smem_base = smem_u32(smem);
+    const float4* in4 = reinterpret_cast<const float4*>(a.in + prob * L.d_in);
+    float* s_pa_base = reinterpret_cast<float*>(smem + c.off_pa);
+    const int cpad = (a.C_in + 7) / 8 * 8;
+    const int Gb = a.CIB >> 3;  // groups of 8 channels per (padded) ci block
+    const uint32_t strip = (uint32_t)W * 16u, plane = (uint32_t)Gb * strip;
+    // MODE 2: segments of source rows (at most ceil(W / up) + 1 of them touch a window)
+    const int nseg = MODE == 2 ? ((W + a.up - 1) / a.up + 1 + 31) >> 5 : (W + 31) >> 5, ntask = Gb * nseg;
+    const long long Tp_in = ntc_tp(a.T_in);
+    const long long ld4 = a.in_ld >> 2;
+    const uint32_t up_magic = 0xFFFFFFFFu / (uint32_t)a.up + 1u;
+    // Tile-invariant geometry.  With up == down == 1 ("direct") the source row of window row r is t0 - halo + r and
+    // t0 is a multiple of 32, so its address splits into (tile base) + (per-thread term of lane - halo) + (per-task
+    // term), the last one read from a shared-memory table: {global offset, smem offset, rows of the segment inside
+    // the window, (g << 16) | first row of the segment}.
+    const bool direct = a.up == 1 && a.down == 1;
+    const int hl = lane - halo;
+    const long long thr_goff = (long long)(hl & ~31) * ld4 + (hl & 31);  // float4 units
+    int4* tab = reinterpret_cast<int4*>(smem + c.off_tab);
+    if constexpr (MODE == 0) {
+      for (int k = tt; k < ntask; k += kTc3XformThreads) {
+        const int g = k / nseg, seg = k - g * nseg;
+        tab[k] = make_int4((int)(seg * 32 * ld4) + g * 64, (int)(g * strip) + seg * 512, W - seg * 32, (g << 16) | (seg * 32));
+      }
+      named_bar_sync(1, kTc3XformThreads);
+    }
+    const uint32_t s_tab = smem_u32(tab);
+    constexpr int CH = kTc3ChunkItems;
+    const int rounds = (ntask + SH::kXW - 1) / SH::kXW;
+    const int n_chunks = (rounds + CH - 1) / CH;
+    const bool has_aff = a.pre_a != nullptr || a.pre_stats != nullptr;
+    // statistics merge: fin_cw channels at a time, fin_P threads (segment phases) per channel
+    const int fin_cw = min(a.C_in, kTc3XformThreads), fin_P = kTc3XformThreads / fin_cw;
+
+    struct Cursor {
+      int m, blk, ch, it, b, tile;  // (b, tile) track m without a division per chunk
+    };
+    const int step_b = step / c.m_tiles, step_t = step - step_b * c.m_tiles;
+    auto advance = [&](Cursor& q) {
+      if (++q.ch == n_chunks) {
+        q.ch = 0;
+        if (++q.blk == a.n_blk) {
+          q.blk = 0;
+          q.m += step;
+          q.b += step_b;
+          q.tile += step_t;
+          if (q.tile >= c.m_tiles) {
+            q.tile -= c.m_tiles;
+            ++q.b;
+          }
+          ++q.it;
+        }
+      }
+    };
+    // Affine buffers are indexed by the number of utterance changes so far (three buffers: a rewrite follows the
+    // named barrier of the previous change, which every thread passes only after converting the tiles before it).
+    int pa_b = -1;
+    uint32_t pa_wbuf = 0;  // affine buffer of the tile being loaded (== utterance changes % 3)
+    int cv_b = -1;
+    auto update_affine = [&](const Cursor& q) {
+      const int b = q.b;
+      if (q.blk == 0 && q.ch == 0 && has_aff && b != pa_b) {
+        pa_b = b;
+        pa_wbuf = pa_wbuf == 2 ? 0 : pa_wbuf + 1;
+        float* s_pa = s_pa_base + pa_wbuf * 2 * cpad;
+        if (a.pre_stats) {
+          // InstanceNorm statistics of utterance b from the producer's per-segment (mean, M2) partials, merged here
+          // in double in a fixed order (fastsvc.py:76,138: biased variance over the time axis, eps inside the sqrt).
+          // Thread (part, ch) accumulates weighted moments of the segment means about the first segment's mean over
+          // every fin_P-th segment; thread ch then adds the parts.
+          double* scr = reinterpret_cast<double*>(smem + c.off_fin);
+          for (int c0 = 0; c0 < a.C_in; c0 += fin_cw) {
+            const int cw = min(fin_cw, a.C_in - c0);
+            const int part = tt / cw, ch = c0 + tt - part * cw;
+            double sw = 0.0, s1 = 0.0, s2 = 0.0, qq = 0.0;
+            if (part < fin_P) {
+              const float2* sp = a.pre_stats + (long long)b * a.pre_nseg * a.C_in + ch;
+              const float pivf = __ldg(sp).x;
+              for (int s0 = part; s0 < a.pre_nseg; s0 += 8 * fin_P) {  // 8 loads in flight, fp32 inside a batch
+                float2 pv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int sg = s0 + u * fin_P;
+                  pv[u] = sg < a.pre_nseg ? __ldg(sp + (long long)sg * a.C_in) : make_float2(pivf, 0.f);
+                }
+                float fw = 0.f, f1 = 0.f, f2 = 0.f, fq = 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int sg = s0 + u * fin_P;
+                  const float nb = sg < a.pre_nseg ? (float)min(32, a.T_in - sg * 32) : 0.f;
+                  const float d = pv[u].x - pivf;
+                  fw += nb;
+                  f1 = fmaf(nb, d, f1);
+                  f2 = fmaf(nb * d, d, f2);
+                  fq += pv[u].y;
+                }
+                sw += (double)fw;
+                s1 += (double)f1;
+                s2 += (double)f2;
+                qq += (double)fq;
+              }
+              double* o = scr + (size_t)(part * cw + (ch - c0)) * 4;
+              o[0] = sw; o[1] = s1; o[2] = s2; o[3] = qq;
+            }
+            named_bar_sync(2, kTc3XformThreads);
+            if (tt < cw) {
+              const int chh = c0 + tt;
+              sw = s1 = s2 = qq = 0.0;
+              for (int pp = 0; pp < fin_P; ++pp) {
+                const double* o = scr + (size_t)(pp * cw + tt) * 4;
+                sw += o[0]; s1 += o[1]; s2 += o[2]; qq += o[3];
+              }
+              const double piv = (double)__ldg(a.pre_stats + (long long)b * a.pre_nseg * a.C_in + chh).x;
+              const double mean = piv + s1 / sw;
+              const double var = fmax(qq + s2 - s1 * s1 / sw, 0.0) / sw;
+              const double rstd = 1.0 / sqrt(var + (double)a.pre_eps);
+              const double e = a.pre_e ? (double)__ldg(a.pre_e + (long long)b * a.C_in + chh) : 0.0;
+              s_pa[chh] = (float)rstd;
+              s_pa[cpad + chh] = (float)(e - mean * rstd);
+            }
+            if (c0 + fin_cw < a.C_in) named_bar_sync(2, kTc3XformThreads);  // scratch reuse by the next channel slab
+          }
+          for (int ch = a.C_in + tt; ch < cpad; ch += kTc3XformThreads) {
+            s_pa[ch] = 1.f;
+            s_pa[cpad + ch] = 0.f;
+          }
+        } else {
+          for (int ch = tt; ch < cpad; ch += kTc3XformThreads) {
+            s_pa[ch] = ch < a.C_in ? __ldg(a.pre_a + (long long)b * a.C_in + ch) : 1.f;
+            s_pa[cpad + ch] = ch < a.C_in ? __ldg(a.pre_c + (long long)b * a.C_in + ch) : 0.f;
+          }
+        }
+      }
+    };
+   if constexpr (MODE == 2) {
+    // ---- MODE 2: nearest-repeat input.  Window row rw <-> output-rate step u = u_lo + rw reads source row u / up,
+    // so a source row s feeds the window rows of steps s*up .. s*up+up-1: load + convert it once, store it `up`
+    // times.  Rows of the window outside [0, T_out) (first / last tile of an utterance) are zero-filled first.
+    const uint32_t seg_magic = 0xFFFFFFFFu / (uint32_t)nseg + 1u;  // exact quotients below 2^16
+    auto tile_rows = [&](const Cursor& q, int& u_lo, int& s_first, int& s_last) {
+      u_lo = q.tile * kTc2M - halo;
+      s_first = (int)__umulhi((uint32_t)max(u_lo, 0), up_magic);
+      s_last = (int)__umulhi((uint32_t)min(u_lo + W - 1, a.T_out - 1), up_magic);
+    };
+    auto load_chunk = [&](const Cursor& q, float4 (&d)[CH][2], uint32_t& live) {
+      live = 0;
+      if (q.m >= n_m) return;
+      update_affine(q);
+      int u_lo, s_first, s_last;
+      tile_rows(q, u_lo, s_first, s_last);
+      const int cg0 = q.blk * Gb;
+      const long long rowbase = (long long)q.b * Tp_in;
+      const int kbase = q.ch * CH * SH::kXW + xw;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int k = kbase + j * SH::kXW;
+        d[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        d[j][1] = d[j][0];
+        if (k < ntask) {  // warp-uniform
+          const int g = nseg == 1 ? k : (int)__umulhi((uint32_t)k, seg_magic), seg = k - g * nseg;
+          const int sr = s_first + seg * 32 + lane;
+          const uint32_t row_ok = sr <= s_last ? 1u : 0u;
+          const uint32_t ok = row_ok & ((cg0 + g) * 8 < a.C_in ? 1u : 0u);
+          const float4* p = in4 + (rowbase + (sr & ~31)) * ld4 + ((sr & 31) + (cg0 + g) * 64);
+          ldg2_pred(p, ok, d[j][0], d[j][1]);
+          live |= row_ok << j;
+        }
+      }
+    };
+    griddep_wait();  // first access to the predecessor's output
+    uint32_t aslot = 0, ause = 0, pa_buf = 0;  // A ring position; affine buffer of the tile being converted
+    const uint32_t sA0 = smem_base + c.off_a + (uint32_t)lane * 16u;
+    const uint32_t s_pa0 = smem_base + c.off_pa;
+    auto convert_chunk = [&](const Cursor& q, const float4 (&d)[CH][2], uint32_t live) {
+      int u_lo, s_first, s_last;
+      tile_rows(q, u_lo, s_first, s_last);
+      if (q.ch == 0) {
+        if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
+        if (q.blk == 0 && has_aff && q.b != cv_b) {  // new utterance: its affine was written one chunk ago
+          cv_b = q.b;
+          pa_buf = pa_buf == 2 ? 0 : pa_buf + 1;
+          named_bar_sync(1, kTc3XformThreads);
+        }
+        if (u_lo < 0 || u_lo + W > a.T_out) {  // zero padding rows of the window (both planes, every group)
+          const uint32_t sz = smem_base + c.off_a + aslot * c.a_bytes;
+          for (int idx = tt; idx < Gb * W; idx += kTc3XformThreads) {
+            const int g = idx / W, rw = idx - g * W, u = u_lo + rw;
+            if (u < 0 || u >= a.T_out) {
+              sts128(sz + (uint32_t)g * strip + (uint32_t)rw * 16u, make_uint4(0u, 0u, 0u, 0u));
+              sts128(sz + plane + (uint32_t)g * strip + (uint32_t)rw * 16u, make_uint4(0u, 0u, 0u, 0u));
+            }
+          }
+        }
+      }
+      const uint32_t sA = smem_base + c.off_a + aslot * c.a_bytes;
+      const uint32_t s_pa = s_pa0 + pa_buf * (uint32_t)(2 * cpad) * 4u + (uint32_t)(q.blk * Gb) * 32u;
+      const uint32_t s_pc = s_pa + (uint32_t)cpad * 4u;
+      const int cg0 = q.blk * Gb;
+      const int kbase = q.ch * CH * SH::kXW + xw;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int k = kbase + j * SH::kXW;
+        if (k < ntask) {  // warp-uniform
+          const int g = nseg == 1 ? k : (int)__umulhi((uint32_t)k, seg_magic), seg = k - g * nseg;
+          float v[8] = {d[j][0].x, d[j][0].y, d[j][0].z, d[j][0].w, d[j][1].x, d[j][1].y, d[j][1].z, d[j][1].w};
+          if ((cg0 + g) * 8 < a.C_in) {  // channel padding of the last ci block stays zero
+            if (has_aff) {
+              const uint32_t ca = (uint32_t)g * 32u;
+              const float4 a0 = lds128f(s_pa + ca), a1 = lds128f(s_pa + ca + 16u);
+              const float4 c0 = lds128f(s_pc + ca), c1 = lds128f(s_pc + ca + 16u);
+              v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
+              v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
+              v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
+              v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+            }
+            if (a.pre_lrelu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
+            }
+          }
+          uint4 hi, lo;
+          split_bf16(v, hi, lo);
+          const int sr = s_first + seg * 32 + lane;
+          const int rw0 = sr * a.up - u_lo;  // window row of the first step this source row feeds
+          const int rw_end = min(W, a.T_out - u_lo);
+          const uint32_t dst = sA + (uint32_t)g * strip;
+          if ((live >> j) & 1u) {
+            for (int i = 0; i < a.up; ++i) {
+              const int rw = rw0 + i;
+              if (rw >= 0 && rw < rw_end) {
+                sts128(dst + (uint32_t)rw * 16u, hi);
+                sts128(dst + plane + (uint32_t)rw * 16u, lo);
+              }
+            }
+          }
+        }
+      }
+      if (q.ch == n_chunks - 1) {
+        fence_proxy_async();
+        mbar_arrive(bars + kBarAFull + aslot);
+        if (++aslot == (uint32_t)c.a_slots) {
+          aslot = 0;
+          ++ause;
+        }
+      }
+    };
+    // software pipeline over the chunk sequence: chunk k+1 is in flight while chunk k is converted
+    Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
+    float4 dc[CH][2], dn[CH][2];
+    uint32_t live_c, live_n;
+    load_chunk(cur, dc, live_c);
+    while (cur.m < n_m) {
+      Cursor nxt = cur;
+      advance(nxt);
+      load_chunk(nxt, dn, live_n);
+      convert_chunk(cur, dc, live_c);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        dc[j][0] = dn[j][0];
+        dc[j][1] = dn[j][1];
+      }
+      live_c = live_n;
+      cur = nxt;
+    }
+   } else {
+    // issue the loads of one chunk (no use of the results); bit j of `live`: this lane's row of task j is real data
+    auto load_chunk = [&](const Cursor& q, float4 (&d)[CH][2], uint32_t& live) {
+      live = 0;
+      if (q.m >= n_m) return;
+      const int b = q.b;
+      update_affine(q);
+      const int t0 = q.tile * kTc2M, ut = t0 + hl;
+      const int cg0 = q.blk * Gb;
+      const long long rowbase = (long long)b * Tp_in;
+      const float4* tb = in4 + (rowbase + t0) * ld4 + thr_goff + cg0 * 64;
+      const int kbase = q.ch * CH * SH::kXW + xw;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int k = kbase + j * SH::kXW;
+        d[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        d[j][1] = d[j][0];
+        if (k < ntask) {  // warp-uniform
+          const int4 e = lds128i(s_tab + (uint32_t)k * 16u);
+          const int g = e.w >> 16, u = ut + (e.w & 0xffff);
+          const uint32_t ok = (lane < e.z && (unsigned)u < (unsigned)a.T_out && (cg0 + g) * 8 < a.C_in) ? 1u : 0u;
+          const float4* p = tb + e.x;
+          if (!direct) {
+            const int src = max(u, 0) * a.down;  // MODE 0: up == 1
+            p = in4 + (rowbase + (src & ~31)) * ld4 + ((src & 31) + (cg0 + g) * 64);
+          }
+          ldg2_pred(p, ok, d[j][0], d[j][1]);
+          live |= ok << j;
+        }
+      }
+    };
+    griddep_wait();  // first access to the predecessor's output
+    uint32_t aslot = 0, ause = 0, pa_buf = 0;  // A ring position; affine buffer of the tile being converted
+    const uint32_t sA0 = smem_base + c.off_a + (uint32_t)lane * 16u;
+    const uint32_t s_pa0 = smem_base + c.off_pa;
+    auto convert_chunk = [&](const Cursor& q, const float4 (&d)[CH][2], uint32_t live) {
+      if (q.ch == 0) {
+        if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
+        if (q.blk == 0 && has_aff && q.b != cv_b) {  // new utterance: its affine was written one chunk ago
+          cv_b = q.b;
+          pa_buf = pa_buf == 2 ? 0 : pa_buf + 1;  // == (number of utterance changes) % 3, as on the writing side
+          named_bar_sync(1, kTc3XformThreads);
+        }
+      }
+      const uint32_t sA = sA0 + aslot * c.a_bytes;
+      const uint32_t s_pa = s_pa0 + pa_buf * (uint32_t)(2 * cpad) * 4u + (uint32_t)(q.blk * Gb) * 32u;
+      const uint32_t s_pc = s_pa + (uint32_t)cpad * 4u;
+      const int kbase = q.ch * CH * SH::kXW + xw;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        const int k = kbase + j * SH::kXW;
+        if (k < ntask) {  // warp-uniform
+          const int4 e = lds128i(s_tab + (uint32_t)k * 16u);
+          float v[8] = {d[j][0].x, d[j][0].y, d[j][0].z, d[j][0].w, d[j][1].x, d[j][1].y, d[j][1].z, d[j][1].w};
+          if (has_aff) {
+            const uint32_t ca = (uint32_t)(e.w >> 16) * 32u;
+            const float4 a0 = lds128f(s_pa + ca), a1 = lds128f(s_pa + ca + 16u);
+            const float4 c0 = lds128f(s_pc + ca), c1 = lds128f(s_pc + ca + 16u);
+            v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
+            v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
+            v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
+            v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+          }
+          if (a.pre_lrelu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
+          }
+          const uint32_t in_strip = lane < e.z ? 1u : 0u;
+          split_store_p(sA + (uint32_t)e.y, plane, v, in_strip & (live >> j), in_strip & ~(live >> j));
+        }
+      }
+      if (q.ch == n_chunks - 1) {
+        fence_proxy_async();
+        mbar_arrive(bars + kBarAFull + aslot);
+        if (++aslot == (uint32_t)c.a_slots) {
+          aslot = 0;
+          ++ause;
+        }
+      }
+    };
+    // software pipeline over the chunk sequence: chunk k+1 is in flight while chunk k is converted
+    Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
+    float4 dc[CH][2], dn[CH][2];
+    uint32_t live_c, live_n;
+    load_chunk(cur, dc, live_c);
+    while (cur.m < n_m) {
+      Cursor nxt = cur;
+      advance(nxt);
+      load_chunk(nxt, dn, live_n);
+      convert_chunk(cur, dc, live_c);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        dc[j][0] = dn[j][0];
+        dc[j][1] = dn[j][1];
+      }
+      live_c = live_n;
+      cur = nxt;
+    }
+   }
+   }
   } else if (warp >= SH::kE0) {
     // =============================== EPILOGUE ===============================
     const int ew = warp - SH::kE0;
@@ -460,8 +899,8 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     float* raw = a.raw ? a.raw + prob * L.d_raw : nullptr;
     float* out = a.out ? a.out + prob * L.d_out : nullptr;
     const bool has_film = a.gamma != nullptr, has_res = res != nullptr, has_stats = a.stats != nullptr;
-    const uint32_t scr = smem_u32(smem + c.off_scr) + (uint32_t)(ew * 32 * c.scr_pitch) * 4u;
-    const uint32_t scr_row = scr + (uint32_t)(lane * c.scr_pitch) * 4u;
+    const uint32_t scr = smem_u32(smem + c.off_scr) + (uint32_t)(ew * (32 * c.scr_pitch + 16)) * 4u;
+    const uint32_t scr_row = scr + (uint32_t)(lane * c.scr_pitch) * 4u + (lane >= 16 ? 64u : 0u);
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int step_b = step / c.m_tiles, step_t = step - step_b * c.m_tiles;
     const int rl = q * 32 + lane;  // row of this thread inside the tile
@@ -568,9 +1007,10 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         if (sub + 1 < n_sub) load_ops(b, tile, sub + 1);
         else if (m + step < n_m) load_ops(nb, ntile, 0);
         if (has_stats && n_rows_seg > 0) {
-          // (mean, M2) of the stored values over this warp's <= 32 rows, per channel: transpose through the
-          // warp's smem scratch, then lane (half, ch) sums 16 rows about their first sample; the two halves
-          // are merged with Chan's formula.  in_finalize2_kernel merges the segments in double.
+          // (mean, M2) of the stored values over this warp's <= 32 rows, per channel: transpose through the warp's
+          // smem scratch (rows 16..31 shifted by 16 floats so the two half-warps read disjoint banks), then lane
+          // (half, ch) sums its 16 rows about the segment's first sample and the halves are added.
+          // in_finalize2_kernel / the consumer's transform role merge the segments in double.
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -581,22 +1021,22 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
           const int hh = lane >> 4, ch = lane & 15;
           const int cnt = max(0, min(16, n_rows_seg - 16 * hh));
           float piv = 0.f, s1 = 0.f, s2 = 0.f;
-          if (ch < nh && cnt > 0) {
-            const uint32_t colp = scr + (uint32_t)((16 * hh) * c.scr_pitch + ch) * 4u;
+          if (ch < nh) {
             const uint32_t pitch_b = (uint32_t)c.scr_pitch * 4u;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(piv) : "r"(colp));
+            const uint32_t colp = scr + (uint32_t)ch * 4u + (uint32_t)hh * (16u * pitch_b + 64u);
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(piv) : "r"(scr + (uint32_t)ch * 4u));
             if (cnt == 16) {
-              float xv[15];
+              float xv[16];
 #pragma unroll
-              for (int i = 0; i < 15; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[i]) : "r"(colp + (i + 1) * pitch_b));
+              for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[i]) : "r"(colp + i * pitch_b));
 #pragma unroll
-              for (int i = 0; i < 15; ++i) {
+              for (int i = 0; i < 16; ++i) {
                 const float dd = xv[i] - piv;
                 s1 += dd;
                 s2 = fmaf(dd, dd, s2);
               }
             } else {
-              for (int i = 1; i < cnt; ++i) {
+              for (int i = 0; i < cnt; ++i) {
                 float xi;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xi) : "r"(colp + i * pitch_b));
                 const float dd = xi - piv;
@@ -605,18 +1045,12 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
               }
             }
           }
-          const float n1 = (float)cnt;
-          float mean = cnt > 0 ? piv + s1 / n1 : 0.f;
-          float m2 = cnt > 0 ? fmaxf(s2 - s1 * s1 / n1, 0.f) : 0.f;
-          const float mean_o = __shfl_xor_sync(0xffffffffu, mean, 16);
-          const float m2_o = __shfl_xor_sync(0xffffffffu, m2, 16);
-          const float n_o = __shfl_xor_sync(0xffffffffu, n1, 16);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
           if (hh == 0 && ch < nh) {
-            const float nn = n1 + n_o;
-            const float dd = mean_o - mean;
-            mean += dd * n_o / nn;
-            m2 += m2_o + dd * dd * n1 * n_o / nn;
-            st_row[co + ch] = make_float2(mean, m2);
+            const float rn = n_rows_seg >= 32 ? 0.03125f : __frcp_rn((float)n_rows_seg);
+            const float dm = s1 * rn;
+            st_row[co + ch] = make_float2(piv + dm, fmaxf(fmaf(-s1, dm, s2), 0.f));
           }
         }
       }
