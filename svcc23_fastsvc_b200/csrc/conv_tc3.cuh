@@ -51,7 +51,9 @@ struct Tc3Cfg {
   int a_slots;    // depth of the A ring (1..3)
   int scr_pitch;  // floats per row of the per-warp statistics scratch (12 or 20)
   uint32_t a_bytes, b_bytes;  // per ring slot
-  uint32_t off_w, off_a, off_b, off_scr, off_pa, off_fin, off_tab, off_bar, total;
+  uint32_t off_w, off_a, off_b, off_scr, off_pa, off_fin, off_tab, off_stg, off_bar, total;
+  uint32_t stg_bytes;  // one slot of the transform's raw-row staging ring (a chunk: kXW warps x CH tasks x 1 KB)
+  int stg_depth;       // chunks in flight (ring of stg_depth + 1 slots)
 };
 
 struct Tc3Launch {
@@ -60,6 +62,17 @@ struct Tc3Launch {
   Tc3Cfg c;
 };
 
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -107,6 +120,15 @@ __device__ __forceinline__ void split_store_s(uint32_t addr, uint32_t plane, con
   sts128(addr + plane, make_uint4(lo[0], lo[1], lo[2], lo[3]));
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); bytes = 0 writes zeros without reading
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 // bf16 hi|lo split of 8 fp32 values into two packed 16-byte chunks
 __device__ __forceinline__ void split_bf16(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h4[4], l4[4];
@@ -183,8 +205,14 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
   const uint32_t scr_bytes = (small ? 4u : 8u) * (32u * c->scr_pitch + 16u) * 4u;
   const uint32_t budget = small ? 113u * 1024u : 227u * 1024u;
   const uint32_t pa_bytes = 3u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;  // triple-buffered per-utterance affine
-  for (int slots = 3; slots >= 1; --slots) {
+  // Preference: deep staging (loads in flight) first, then A ring depth.
+  const uint32_t xw = small ? 2u : 6u;
+  c->stg_bytes = a.gen_w ? 0u : xw * (uint32_t)kTc3ChunkItems * 1024u;
+  static const int pref[][2] = {{3, 3}, {2, 3}, {3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 1}};  // {a_slots, stg_depth}
+  for (const auto& pr : pref) {
+    const int slots = pr[0];
     c->a_slots = slots;
+    c->stg_depth = a.gen_w ? 0 : pr[1];
     uint32_t off = 0;
     c->off_w = off;
     off += w_bytes;
@@ -201,6 +229,8 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
     off += a.pre_stats ? (uint32_t)(small ? 64 : 192) * 32u : 0u;  // statistics merge scratch: 4 doubles per thread
     c->off_tab = off;
     off += Gb * (uint32_t)((W + 31) / 32) * 16u;  // transform geometry table
+    c->off_stg = off;
+    off += c->stg_bytes * (uint32_t)(c->stg_depth + 1);
     c->off_bar = off;
     off += kBarCount * 8 + 16;
     c->total = off;
@@ -299,56 +329,70 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   }
   if (warp == SH::kMmaWarp) {
     // =============================== MMA ISSUER ===============================
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow and descriptor arithmetic so that it stays in the uniform
+    // datapath; one elected lane issues the tcgen05 instructions.  (With the loop inside `if (lane == 0)` every
+    // descriptor went through per-MMA vector->uniform moves: ~460 instructions per tile, 3000 cycles, the bound of
+    // every 24-channel layer.)
+    {
+      const bool leader = elect_one_sync();
       const uint32_t idesc = umma_idesc_bf16(kTc2M, a.N_tile);
       const uint32_t Gb = (uint32_t)a.CIB >> 3;
       const uint32_t strip = (uint32_t)W * 16u, a_plane = Gb * strip;
       const uint32_t b_strip = (uint32_t)a.N_tile * 16u, b_half = (uint32_t)K * Gb * b_strip;
       const uint32_t a_hiw = (uint32_t)(umma_desc(0, strip, 128) >> 32), b_hiw = (uint32_t)(umma_desc(0, b_strip, 128) >> 32);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t smem_u = smem_u32(smem);
+      const uint32_t n_kc = (uint32_t)a.CIB >> 4;
       if (a.w_resident) mbar_wait2(bars + kBarWFull, 0);
-      uint32_t pa_pos = 0, pbk = 0;
+      uint32_t aslot = 0, ause = 0, pbk = 0;
       int it = 0;
       for (int m = first; m < n_m; m += step, ++it) {
         const uint32_t acc = (uint32_t)it & 1u;
         if (it >= 2) mbar_wait2(bars + kBarAccEmpty + acc, (((uint32_t)it >> 1) + 1) & 1u);
-        const uint32_t d_tmem = tmem + acc * acc_stride;
+        const uint32_t d_tmem = tmem_u + acc * acc_stride;
         for (int blk = 0; blk < a.n_blk; ++blk) {
-          const uint32_t aslot = pa_pos % (uint32_t)c.a_slots, ause = pa_pos / (uint32_t)c.a_slots;
           mbar_wait2(bars + kBarAFull + aslot, ause & 1u);
           uint32_t sB_addr;
           const uint32_t bslot = pbk & 1u;
           if (a.w_resident) {
-            sB_addr = smem_u32(smem + c.off_w + (size_t)blk * c.b_bytes);
+            sB_addr = smem_u + c.off_w + (uint32_t)blk * c.b_bytes;
           } else {
             mbar_wait2(bars + kBarBFull + bslot, (pbk >> 1) & 1u);
-            sB_addr = smem_u32(smem + c.off_b + bslot * c.b_bytes);
+            sB_addr = smem_u + c.off_b + bslot * c.b_bytes;
           }
           tc_fence_after();
-          const uint32_t sA_addr = smem_u32(smem + c.off_a + aslot * c.a_bytes);
+          const uint32_t sA_addr = smem_u + c.off_a + aslot * c.a_bytes;
           // descriptors differ only in the 14-bit start-address field of the low word (addresses < 256 KB)
           const uint32_t a_w0 = (uint32_t)umma_desc(sA_addr, strip, 128), b_w0 = (uint32_t)umma_desc(sB_addr, b_strip, 128);
+#pragma unroll
           for (int k = 0; k < K; ++k) {
             uint32_t a_w = a_w0 + (uint32_t)(k * a.dil), b_w = b_w0 + (((uint32_t)k * Gb * b_strip) >> 4);
-            for (uint32_t kc = 0; kc < (uint32_t)a.CIB / 16u; ++kc) {
+            for (uint32_t kc = 0; kc < n_kc; ++kc) {
               const uint64_t a_hi = ((uint64_t)a_hiw << 32) | a_w, a_lo = ((uint64_t)a_hiw << 32) | (a_w + (a_plane >> 4));
               const uint64_t b_hi = ((uint64_t)b_hiw << 32) | b_w, b_lo = ((uint64_t)b_hiw << 32) | (b_w + (b_half >> 4));
               const uint32_t accum = (blk == 0 && k == 0 && kc == 0) ? 0u : 1u;
-              umma_bf16(d_tmem, a_lo, b_hi, idesc, accum);  // small terms first, then the dominant one
-              umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+              if (leader) {
+                umma_bf16(d_tmem, a_lo, b_hi, idesc, accum);  // small terms first, then the dominant one
+                umma_bf16(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_bf16(d_tmem, a_hi, b_hi, idesc, 1u);
+              }
               a_w += (2u * strip) >> 4;
               b_w += (2u * b_strip) >> 4;
             }
           }
-          umma_commit(bars + kBarAEmpty + aslot);
-          if (!a.w_resident) {
-            umma_commit(bars + kBarBEmpty + bslot);
-            ++pbk;
+          if (leader) {
+            umma_commit(bars + kBarAEmpty + aslot);
+            if (!a.w_resident) umma_commit(bars + kBarBEmpty + bslot);
+            if (blk == a.n_blk - 1) umma_commit(bars + kBarAccFull + acc);
           }
-          if (blk == a.n_blk - 1) umma_commit(bars + kBarAccFull + acc);
-          ++pa_pos;
+          if (!a.w_resident) ++pbk;
+          if (++aslot == (uint32_t)c.a_slots) {
+            aslot = 0;
+            ++ause;
+          }
         }
       }
+      __syncwarp();
     }
   } else if (warp >= SH::kX0 && warp < SH::kE0) {
    if constexpr (GEN) {
@@ -550,6 +594,8 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       named_bar_sync(1, kTc3XformThreads);
     }
     const uint32_t s_tab = smem_u32(tab);
+    // staging ring: slot = one chunk; per task 2 x 512 B (the two 4-channel halves), lane-private 16 B pieces
+    const uint32_t stg0 = smem_base + c.off_stg + (uint32_t)xw * (kTc3ChunkItems * 1024u) + (uint32_t)lane * 16u;
     constexpr int CH = kTc3ChunkItems;
     const int rounds = (ntask + SH::kXW - 1) / SH::kXW;
     const int n_chunks = (rounds + CH - 1) / CH;
@@ -667,36 +713,35 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       s_first = (int)__umulhi((uint32_t)max(u_lo, 0), up_magic);
       s_last = (int)__umulhi((uint32_t)min(u_lo + W - 1, a.T_out - 1), up_magic);
     };
-    auto load_chunk = [&](const Cursor& q, float4 (&d)[CH][2], uint32_t& live) {
-      live = 0;
-      if (q.m >= n_m) return;
-      update_affine(q);
-      int u_lo, s_first, s_last;
-      tile_rows(q, u_lo, s_first, s_last);
-      const int cg0 = q.blk * Gb;
-      const long long rowbase = (long long)q.b * Tp_in;
-      const int kbase = q.ch * CH * SH::kXW + xw;
+    auto issue_chunk = [&](const Cursor& q, uint32_t slot) {
+      if (q.m < n_m) {
+        int u_lo, s_first, s_last;
+        tile_rows(q, u_lo, s_first, s_last);
+        const int cg0 = q.blk * Gb;
+        const long long rowbase = (long long)q.b * Tp_in;
+        const int kbase = q.ch * CH * SH::kXW + xw;
+        const uint32_t dst0 = stg0 + slot * c.stg_bytes;
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        const int k = kbase + j * SH::kXW;
-        d[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        d[j][1] = d[j][0];
-        if (k < ntask) {  // warp-uniform
-          const int g = nseg == 1 ? k : (int)__umulhi((uint32_t)k, seg_magic), seg = k - g * nseg;
-          const int sr = s_first + seg * 32 + lane;
-          const uint32_t row_ok = sr <= s_last ? 1u : 0u;
-          const uint32_t ok = row_ok & ((cg0 + g) * 8 < a.C_in ? 1u : 0u);
-          const float4* p = in4 + (rowbase + (sr & ~31)) * ld4 + ((sr & 31) + (cg0 + g) * 64);
-          ldg2_pred(p, ok, d[j][0], d[j][1]);
-          live |= row_ok << j;
+        for (int j = 0; j < CH; ++j) {
+          const int k = kbase + j * SH::kXW;
+          if (k < ntask) {  // warp-uniform
+            const int g = nseg == 1 ? k : (int)__umulhi((uint32_t)k, seg_magic), seg = k - g * nseg;
+            const int sr = s_first + seg * 32 + lane;
+            const bool ok = sr <= s_last && (cg0 + g) * 8 < a.C_in;
+            const float4* p = ok ? in4 + (rowbase + (sr & ~31)) * ld4 + ((sr & 31) + (cg0 + g) * 64) : in4;
+            cp_async16(dst0 + (uint32_t)j * 1024u, p, ok ? 16u : 0u);
+            cp_async16(dst0 + (uint32_t)j * 1024u + 512u, p + (ok ? 32 : 0), ok ? 16u : 0u);
+          }
         }
       }
+      cp_async_commit();
     };
     griddep_wait();  // first access to the predecessor's output
     uint32_t aslot = 0, ause = 0, pa_buf = 0;  // A ring position; affine buffer of the tile being converted
     const uint32_t sA0 = smem_base + c.off_a + (uint32_t)lane * 16u;
     const uint32_t s_pa0 = smem_base + c.off_pa;
-    auto convert_chunk = [&](const Cursor& q, const float4 (&d)[CH][2], uint32_t live) {
+    auto convert_chunk = [&](const Cursor& q, uint32_t slot) {
+      const uint32_t src0 = stg0 + slot * c.stg_bytes;
       int u_lo, s_first, s_last;
       tile_rows(q, u_lo, s_first, s_last);
       if (q.ch == 0) {
@@ -727,7 +772,8 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         const int k = kbase + j * SH::kXW;
         if (k < ntask) {  // warp-uniform
           const int g = nseg == 1 ? k : (int)__umulhi((uint32_t)k, seg_magic), seg = k - g * nseg;
-          float v[8] = {d[j][0].x, d[j][0].y, d[j][0].z, d[j][0].w, d[j][1].x, d[j][1].y, d[j][1].z, d[j][1].w};
+          const float4 dA = lds128f(src0 + (uint32_t)j * 1024u), dB = lds128f(src0 + (uint32_t)j * 1024u + 512u);
+          float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
           if ((cg0 + g) * 8 < a.C_in) {  // channel padding of the last ci block stays zero
             if (has_aff) {
               const uint32_t ca = (uint32_t)g * 32u;
@@ -749,7 +795,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
           const int rw0 = sr * a.up - u_lo;  // window row of the first step this source row feeds
           const int rw_end = min(W, a.T_out - u_lo);
           const uint32_t dst = sA + (uint32_t)g * strip;
-          if ((live >> j) & 1u) {
+          if (sr <= s_last) {
             for (int i = 0; i < a.up; ++i) {
               const int rw = rw0 + i;
               if (rw >= 0 && rw < rw_end) {
@@ -769,60 +815,73 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         }
       }
     };
-    // software pipeline over the chunk sequence: chunk k+1 is in flight while chunk k is converted
-    Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
-    float4 dc[CH][2], dn[CH][2];
-    uint32_t live_c, live_n;
-    load_chunk(cur, dc, live_c);
-    while (cur.m < n_m) {
-      Cursor nxt = cur;
-      advance(nxt);
-      load_chunk(nxt, dn, live_n);
-      convert_chunk(cur, dc, live_c);
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        dc[j][0] = dn[j][0];
-        dc[j][1] = dn[j][1];
+    // Software pipeline over the chunk sequence: the raw rows of the next `stg_depth` chunks are in flight (cp.async
+    // into a per-lane staging ring, so no registers are tied up and no barrier is needed: a lane reads back only what
+    // it copied itself) while chunk i is converted.  The InstanceNorm affine is prepared one chunk ahead.
+    {
+      Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
+      Cursor ahead = cur;
+      const int depth = c.stg_depth;
+      uint32_t slot_i = 0, slot_c = 0;
+      for (int i = 0; i < depth; ++i) {
+        issue_chunk(ahead, slot_i);
+        slot_i = slot_i + 1 == (uint32_t)depth + 1 ? 0 : slot_i + 1;
+        advance(ahead);
       }
-      live_c = live_n;
-      cur = nxt;
+      if (cur.m < n_m) update_affine(cur);
+      while (cur.m < n_m) {
+        issue_chunk(ahead, slot_i);
+        slot_i = slot_i + 1 == (uint32_t)depth + 1 ? 0 : slot_i + 1;
+        advance(ahead);
+        Cursor nxt = cur;
+        advance(nxt);
+        if (nxt.m < n_m) update_affine(nxt);
+        if (depth == 3) cp_async_wait<3>();
+        else if (depth == 2) cp_async_wait<2>();
+        else cp_async_wait<1>();
+        convert_chunk(cur, slot_c);
+        slot_c = slot_c + 1 == (uint32_t)depth + 1 ? 0 : slot_c + 1;
+        cur = nxt;
+      }
+      cp_async_wait<0>();
     }
    } else {
     // issue the loads of one chunk (no use of the results); bit j of `live`: this lane's row of task j is real data
-    auto load_chunk = [&](const Cursor& q, float4 (&d)[CH][2], uint32_t& live) {
-      live = 0;
-      if (q.m >= n_m) return;
-      const int b = q.b;
-      update_affine(q);
-      const int t0 = q.tile * kTc2M, ut = t0 + hl;
-      const int cg0 = q.blk * Gb;
-      const long long rowbase = (long long)b * Tp_in;
-      const float4* tb = in4 + (rowbase + t0) * ld4 + thr_goff + cg0 * 64;
-      const int kbase = q.ch * CH * SH::kXW + xw;
+    auto issue_chunk = [&](const Cursor& q, uint32_t slot) {
+      if (q.m < n_m) {
+        const int t0 = q.tile * kTc2M, ut = t0 + hl;
+        const int cg0 = q.blk * Gb;
+        const long long rowbase = (long long)q.b * Tp_in;
+        const float4* tb = in4 + (rowbase + t0) * ld4 + thr_goff + cg0 * 64;
+        const int kbase = q.ch * CH * SH::kXW + xw;
+        const uint32_t dst0 = stg0 + slot * c.stg_bytes;
 #pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        const int k = kbase + j * SH::kXW;
-        d[j][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        d[j][1] = d[j][0];
-        if (k < ntask) {  // warp-uniform
-          const int4 e = lds128i(s_tab + (uint32_t)k * 16u);
-          const int g = e.w >> 16, u = ut + (e.w & 0xffff);
-          const uint32_t ok = (lane < e.z && (unsigned)u < (unsigned)a.T_out && (cg0 + g) * 8 < a.C_in) ? 1u : 0u;
-          const float4* p = tb + e.x;
-          if (!direct) {
-            const int src = max(u, 0) * a.down;  // MODE 0: up == 1
-            p = in4 + (rowbase + (src & ~31)) * ld4 + ((src & 31) + (cg0 + g) * 64);
+        for (int j = 0; j < CH; ++j) {
+          const int k = kbase + j * SH::kXW;
+          if (k < ntask) {  // warp-uniform
+            const int4 e = lds128i(s_tab + (uint32_t)k * 16u);
+            const int g = e.w >> 16, u = ut + (e.w & 0xffff);
+            const bool ok = lane < e.z && (unsigned)u < (unsigned)a.T_out && (cg0 + g) * 8 < a.C_in;
+            const float4* p = tb + e.x;
+            if (!direct) {
+              const int src = max(u, 0) * a.down;  // MODE 0: up == 1
+              p = in4 + (rowbase + (src & ~31)) * ld4 + ((src & 31) + (cg0 + g) * 64);
+            }
+            if (!ok) p = in4;
+            cp_async16(dst0 + (uint32_t)j * 1024u, p, ok ? 16u : 0u);
+            cp_async16(dst0 + (uint32_t)j * 1024u + 512u, p + (ok ? 32 : 0), ok ? 16u : 0u);
           }
-          ldg2_pred(p, ok, d[j][0], d[j][1]);
-          live |= ok << j;
         }
       }
+      cp_async_commit();
     };
     griddep_wait();  // first access to the predecessor's output
     uint32_t aslot = 0, ause = 0, pa_buf = 0;  // A ring position; affine buffer of the tile being converted
     const uint32_t sA0 = smem_base + c.off_a + (uint32_t)lane * 16u;
     const uint32_t s_pa0 = smem_base + c.off_pa;
-    auto convert_chunk = [&](const Cursor& q, const float4 (&d)[CH][2], uint32_t live) {
+    auto convert_chunk = [&](const Cursor& q, uint32_t slot) {
+      const uint32_t src0 = stg0 + slot * c.stg_bytes;
+      const int ut = q.tile * kTc2M + hl;
       if (q.ch == 0) {
         if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
         if (q.blk == 0 && has_aff && q.b != cv_b) {  // new utterance: its affine was written one chunk ago
@@ -840,7 +899,8 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         const int k = kbase + j * SH::kXW;
         if (k < ntask) {  // warp-uniform
           const int4 e = lds128i(s_tab + (uint32_t)k * 16u);
-          float v[8] = {d[j][0].x, d[j][0].y, d[j][0].z, d[j][0].w, d[j][1].x, d[j][1].y, d[j][1].z, d[j][1].w};
+          const float4 dA = lds128f(src0 + (uint32_t)j * 1024u), dB = lds128f(src0 + (uint32_t)j * 1024u + 512u);
+          float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
           if (has_aff) {
             const uint32_t ca = (uint32_t)(e.w >> 16) * 32u;
             const float4 a0 = lds128f(s_pa + ca), a1 = lds128f(s_pa + ca + 16u);
@@ -854,8 +914,10 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
           }
+          // rows outside the utterance and the channel padding of the last ci block are zero AFTER the prologue
           const uint32_t in_strip = lane < e.z ? 1u : 0u;
-          split_store_p(sA + (uint32_t)e.y, plane, v, in_strip & (live >> j), in_strip & ~(live >> j));
+          const uint32_t real = ((unsigned)(ut + (e.w & 0xffff)) < (unsigned)a.T_out && (q.blk * Gb + (e.w >> 16)) * 8 < a.C_in) ? 1u : 0u;
+          split_store_p(sA + (uint32_t)e.y, plane, v, in_strip & real, in_strip & ~real);
         }
       }
       if (q.ch == n_chunks - 1) {
@@ -867,23 +929,35 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         }
       }
     };
-    // software pipeline over the chunk sequence: chunk k+1 is in flight while chunk k is converted
-    Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
-    float4 dc[CH][2], dn[CH][2];
-    uint32_t live_c, live_n;
-    load_chunk(cur, dc, live_c);
-    while (cur.m < n_m) {
-      Cursor nxt = cur;
-      advance(nxt);
-      load_chunk(nxt, dn, live_n);
-      convert_chunk(cur, dc, live_c);
-#pragma unroll
-      for (int j = 0; j < CH; ++j) {
-        dc[j][0] = dn[j][0];
-        dc[j][1] = dn[j][1];
+    // Software pipeline over the chunk sequence: the raw rows of the next `stg_depth` chunks are in flight (cp.async
+    // into a per-lane staging ring, so no registers are tied up and no barrier is needed: a lane reads back only what
+    // it copied itself) while chunk i is converted.  The InstanceNorm affine is prepared one chunk ahead.
+    {
+      Cursor cur{first, 0, 0, 0, first / c.m_tiles, first % c.m_tiles};
+      Cursor ahead = cur;
+      const int depth = c.stg_depth;
+      uint32_t slot_i = 0, slot_c = 0;
+      for (int i = 0; i < depth; ++i) {
+        issue_chunk(ahead, slot_i);
+        slot_i = slot_i + 1 == (uint32_t)depth + 1 ? 0 : slot_i + 1;
+        advance(ahead);
       }
-      live_c = live_n;
-      cur = nxt;
+      if (cur.m < n_m) update_affine(cur);
+      while (cur.m < n_m) {
+        issue_chunk(ahead, slot_i);
+        slot_i = slot_i + 1 == (uint32_t)depth + 1 ? 0 : slot_i + 1;
+        advance(ahead);
+        Cursor nxt = cur;
+        advance(nxt);
+        if (nxt.m < n_m) update_affine(nxt);
+        if (depth == 3) cp_async_wait<3>();
+        else if (depth == 2) cp_async_wait<2>();
+        else cp_async_wait<1>();
+        convert_chunk(cur, slot_c);
+        slot_c = slot_c + 1 == (uint32_t)depth + 1 ? 0 : slot_c + 1;
+        cur = nxt;
+      }
+      cp_async_wait<0>();
     }
    }
    }
