@@ -155,6 +155,23 @@ int fsvc_forward_profile(fsvc_handle* h, const float* ppg, const float* sine, co
                          void* stream, fsvc_kernel_record* records, int capacity, int* count);
 
 /* Number of kernels the last fsvc_forward on this handle enqueued. */
+/*
+ * Sine excitation, batched: replaces SignalGenerator.sinusoid (harana/utils/features.py:178-197), the step that
+ * feeds `sine` of fsvc_forward; called once per utterance at batch 1 by FastSVCGenerator.inference
+ * (fastsvc.py:381) and decode_fastsvc.py:182-186.
+ *   f0    [B][frames] Hz, 0 = unvoiced;  noise [B][frames*hop] standard normal draws (the reference makes them with
+ *   torch.randn inside the call, features.py:194) or NULL when noise_amp == 0;  out [B][frames*hop].
+ * The phase is the reference's CPU cumsum (double accumulation, fp32 outputs); results match it to <= 2e-6.
+ */
+int fsvc_sine_excitation(const float* f0, const float* noise, float* out, int B, int frames, int hop,
+                         float sample_rate, float sine_amp, float noise_amp, void* stream);
+
+/*
+ * Waveform -> PCM-16 as soundfile.write(..., "PCM_16") stores it (decode_fastsvc.py:193-198): lrintf(x * 32767),
+ * saturating. x, y: device pointers to n samples.
+ */
+int fsvc_pcm16(const float* x, int16_t* y, long long n, void* stream);
+
 int fsvc_last_launch_count(const fsvc_handle* h);
 
 #ifdef __cplusplus

@@ -22,6 +22,7 @@ EXPORTS = (
     "fsvc_weight_tensor_info", "fsvc_set_weights", "fsvc_workspace_bytes", "fsvc_forward",
     "fsvc_host_io_bytes", "fsvc_forward_host", "fsvc_downsample_forward", "fsvc_film_forward",
     "fsvc_upsample_forward", "fsvc_block_workspace_bytes", "fsvc_last_launch_count", "fsvc_forward_profile",
+    "fsvc_sine_excitation", "fsvc_pcm16",
 )
 
 
@@ -97,6 +98,10 @@ def load():
     lib.fsvc_forward_profile.restype = i32
     lib.fsvc_forward_profile.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, i32, vp,
                                          ctypes.POINTER(KernelRecord), i32, ctypes.POINTER(i32)]
+    lib.fsvc_sine_excitation.restype = i32
+    lib.fsvc_sine_excitation.argtypes = [vp, vp, vp, i32, i32, i32, fp, fp, fp, vp]
+    lib.fsvc_pcm16.restype = i32
+    lib.fsvc_pcm16.argtypes = [vp, vp, ctypes.c_longlong, vp]
     lib.fsvc_last_launch_count.restype = i32
     lib.fsvc_last_launch_count.argtypes = [vp]
     if lib.fsvc_abi_version() != 1:

@@ -14,6 +14,7 @@
 #include "conv_tc2.cuh"
 #include "conv_tc3.cuh"
 #include "level_fused.cuh"
+#include "excitation.cuh"
 
 namespace fsvc {
 
@@ -1533,6 +1534,39 @@ int fsvc_upsample_forward(const float* x, const float* s_scale, const float* s_s
   add2_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, s>>>(s_shift, l_shift, beta, ne);
   if (spk) spk_project_kernel<<<B, 256, 0, s>>>(spk, spk_emb_size, w[12], w[13], c, e);
   run_stage(ctx, sw, x, T, scale, gamma, beta, (long long)c * To, spk ? e : nullptr, sb, out);
+  FSVC_CUDA(cudaGetLastError());
+  return FSVC_OK;
+}
+
+// ---- excitation (before the generator) and PCM-16 quantisation (after it) ---------------------------
+int fsvc_sine_excitation(const float* f0, const float* noise, float* out, int B, int frames, int hop,
+                         float sample_rate, float sine_amp, float noise_amp, void* stream) {
+  if (!f0 || !out || B < 0 || frames < 0 || hop < 1 || hop > 4096 || !(sample_rate > 0.f))
+    return fail(FSVC_E_INVALID, "fsvc_sine_excitation: bad arguments (B=%d frames=%d hop=%d)", B, frames, hop);
+  if (noise_amp > 0.f && !noise) return fail(FSVC_E_INVALID, "fsvc_sine_excitation: noise_amp > 0 needs a noise buffer");
+  if (B == 0 || frames == 0) return FSVC_OK;
+  if (B > 65535) return fail(FSVC_E_INVALID, "fsvc_sine_excitation: at most 65535 utterances per call");
+  ExcArgs a;
+  a.f0 = f0;
+  a.noise = noise_amp > 0.f ? noise : nullptr;
+  a.out = out;
+  a.B = B;
+  a.frames = frames;
+  a.hop = hop;
+  a.sample_rate = sample_rate;
+  a.sine_amp = sine_amp;
+  a.noise_amp = noise_amp;
+  sine_excitation_kernel<<<dim3((frames + kExcFrames - 1) / kExcFrames, B), kExcThreads, 0, (cudaStream_t)stream>>>(a);
+  FSVC_CUDA(cudaGetLastError());
+  return FSVC_OK;
+}
+
+int fsvc_pcm16(const float* x, int16_t* y, long long n, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !y))) return fail(FSVC_E_INVALID, "fsvc_pcm16: bad arguments");
+  if (n == 0) return FSVC_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pcm16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, y, n);
   FSVC_CUDA(cudaGetLastError());
   return FSVC_OK;
 }
