@@ -57,22 +57,41 @@ def write_wav(path, pcm, sampling_rate):
 
 
 class _Staging:
-    """One pinned host staging set + its device mirror + events (two of these are used alternately)."""
+    """One pinned host staging set + its device mirror + events (two of these are used alternately).
 
-    def __init__(self, max_batch, frames, hop, in_channels, device):
-        T = frames * hop
-        pin = dict(pin_memory=True)
-        self.ppg = torch.empty((max_batch, in_channels, frames), dtype=torch.float32, **pin)
-        self.f0 = torch.empty((max_batch, 1, frames), dtype=torch.float32, **pin)
-        self.lft = torch.empty((max_batch, 1, T), dtype=torch.float32, **pin)
-        self.pcm = torch.empty((max_batch, T), dtype=torch.int16, **pin)
-        self.d_ppg = torch.empty_like(self.ppg, device=device)
-        self.d_f0 = torch.empty_like(self.f0, device=device)
-        self.d_lft = torch.empty_like(self.lft, device=device)
+    Buffers are flat, grow-only and re-viewed per utterance length.  They are never freed while work is in flight:
+    device memory released to the caching allocator could be handed to a tensor of the compute stream while the
+    copy stream still writes it (the allocator only orders reuse within one stream), so growth synchronises first."""
+
+    def __init__(self, max_batch, hop, in_channels, device):
+        self.capacity, self.hop, self.cin, self.device = max_batch, hop, in_channels, device
+        self.cap_frames = 0
         self.h2d_done = torch.cuda.Event()
         self.d2h_done = torch.cuda.Event()
         self.consumed = torch.cuda.Event()  # compute no longer reads the device mirrors
-        self.frames, self.capacity = frames, max_batch
+
+    def shape(self, frames):
+        if frames > self.cap_frames:
+            torch.cuda.synchronize(self.device)
+            B, T = self.capacity, frames * self.hop
+            self._ppg = torch.empty(B * self.cin * frames, dtype=torch.float32, pin_memory=True)
+            self._f0 = torch.empty(B * frames, dtype=torch.float32, pin_memory=True)
+            self._lft = torch.empty(B * T, dtype=torch.float32, pin_memory=True)
+            self._pcm = torch.empty(B * T, dtype=torch.int16, pin_memory=True)
+            self._d_ppg = torch.empty(B * self.cin * frames, dtype=torch.float32, device=self.device)
+            self._d_f0 = torch.empty(B * frames, dtype=torch.float32, device=self.device)
+            self._d_lft = torch.empty(B * T, dtype=torch.float32, device=self.device)
+            self.cap_frames = frames
+        B, T = self.capacity, frames * self.hop
+        self.frames = frames
+        self.ppg = self._ppg[:B * self.cin * frames].view(B, self.cin, frames)
+        self.f0 = self._f0[:B * frames].view(B, 1, frames)
+        self.lft = self._lft[:B * T].view(B, 1, T)
+        self.pcm = self._pcm[:B * T].view(B, T)
+        self.d_ppg = self._d_ppg[:B * self.cin * frames].view(B, self.cin, frames)
+        self.d_f0 = self._d_f0[:B * frames].view(B, 1, frames)
+        self.d_lft = self._d_lft[:B * T].view(B, 1, T)
+        return self
 
 
 class BatchConverter:
@@ -102,12 +121,9 @@ class BatchConverter:
 
     # ---- host side -------------------------------------------------------------------------------------------
     def _staging(self, frames, slot):
-        key = (frames, slot)
-        if key not in self._stage:
-            for k in [k for k in self._stage if k[1] == slot and k[0] != frames]:
-                del self._stage[k]  # one length at a time per slot: bounded pinned memory
-            self._stage[key] = _Staging(self.max_batch, frames, self.g.hop_size, self.g.in_channels, self.device)
-        return self._stage[key]
+        if slot not in self._stage:
+            self._stage[slot] = _Staging(self.max_batch, self.g.hop_size, self.g.in_channels, self.device)
+        return self._stage[slot].shape(frames)
 
     def _pack(self, st, utts, src_stats, trg_stats):
         hop = self.g.hop_size

@@ -841,6 +841,7 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
       fa.slope = c.slope;
       const int items = B * fa.n_tiles;
       const int grid = items < h->num_sms ? items : h->num_sms;
+      if (level_fused_fill_desc(&fa) != 0) return fail(FSVC_E_INVALID, "internal: fused level descriptor table overflow");
       launch_pdl(level0_fused_kernel, dim3(grid), kLfThreads, LF.total, stream, fa);
       const double BT = (double)B * T_l;
       c.launched("fused_level", 2.0 * BT * C * (2.0 * (3 + 1 + 9.0 * C) + 2.0 * 9 * C + 12.0 * C),

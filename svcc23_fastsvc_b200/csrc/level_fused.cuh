@@ -83,7 +83,12 @@ struct LevelFusedArgs {
   int N1;                    // N of the C->C convs (multiple of 16, <= 32)
   int N2;                    // N of film_out (multiple of 16, <= 64)
   float slope;
+  // UMMA descriptor low words (start address relative to the dynamic shared-memory base | leading byte offset) of
+  // every (layer, branch, M-tile, tap, K chunk) in issue order: a_hi, a_lo, [w_hi | w_lo].  They live in the kernel
+  // parameters (constant bank) so the issuing warp reads them straight into uniform registers.
+  uint32_t desc[3 * 96];
 };
+constexpr int kLfMaxDesc = 96;
 
 struct LevelFusedSmem {
   uint32_t off_w_c2[2], off_w_c4[2], off_w_film[2], off_w_out, off_buf[4], off_zero, off_sig, off_par, off_desc, off_bar, total;
@@ -112,6 +117,57 @@ __host__ __device__ inline LevelFusedSmem level_fused_smem(int C, int Gp, int N1
   s.off_bar = off; off += 8 * 8 + 16;
   s.total = off;
   return s;
+}
+
+// Descriptor low words of chunk e (issue order), addresses relative to the shared-memory base.  Every (layer, branch,
+// M-tile, tap, K chunk) uses the same shared-memory addresses for every work item.
+__host__ __device__ inline uint32_t lf_desc_lo(uint32_t addr, uint32_t lbo) {
+  return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16);
+}
+__host__ inline int level_fused_fill_desc(LevelFusedArgs* p) {
+  const int C = p->C, G = C >> 3, Gp = p->Gp;
+  const LevelFusedSmem L = level_fused_smem(C, Gp, p->N1, p->N2);
+  const uint32_t strip = kLfRows * 16u, plane = (uint32_t)G * strip, buf_bytes = L.buf_bytes;
+  const uint32_t n1 = 3u * (uint32_t)(Gp / 2), G2 = 2u * (uint32_t)G, n2 = 3u * (G2 / 2);
+  const uint32_t n_chain = 6u * 2u * n1, n_all = n_chain + 2u * n2;
+  if (n_all > (uint32_t)kLfMaxDesc) return -1;
+  const uint32_t buf0 = L.off_buf[0], zero_addr = L.off_zero, w_base = 0;
+  for (uint32_t e = 0; e < n_all; ++e) {
+    uint32_t a0, a1h, a1l, b_addr, b_grp;
+    if (e < n_chain) {
+      const uint32_t lb = e / (2u * n1), r = e - lb * 2u * n1;
+      const int layer = (int)(lb >> 1), br = (int)(lb & 1u);
+      const int mt = (int)(r / n1), kk = (int)(r - (uint32_t)mt * n1);
+      const int k = kk / (Gp / 2), kc = kk - k * (Gp / 2);
+      const int s0 = layer == 0 ? -6 : (layer == 1 ? -2 : -1), d = layer == 0 ? 2 : (layer == 1 ? 4 : 1);
+      const int src = layer == 1 ? 1 : 0;  // a1 / y live in X (0), a2 in Y (1)
+      const uint32_t w_addr = w_base + (layer == 0 ? L.off_w_c2[br] : (layer == 1 ? L.off_w_c4[br] : L.off_w_film[br]));
+      const uint32_t rbytes = (uint32_t)(s0 + kLfHalo - d + k * d + 128 * mt) * 16u;
+      const int g0 = 2 * kc, g1 = g0 + 1;
+      a0 = buf0 + (uint32_t)(2 * br + src) * buf_bytes + (uint32_t)g0 * strip + rbytes;
+      // second 8-channel column: the next real group, or the shared zero strip for the K padding
+      a1h = g1 < G ? a0 + strip : zero_addr + rbytes;
+      a1l = g1 < G ? a0 + plane + strip : zero_addr + rbytes;
+      b_grp = 2u * (uint32_t)p->N1 * 16u;
+      b_addr = w_addr + ((uint32_t)k * Gp + g0) * b_grp;
+    } else {
+      const uint32_t r = e - n_chain;
+      const int mt = (int)(r / n2), kk = (int)(r - (uint32_t)mt * n2);
+      const int k = kk / (int)(G2 / 2);
+      const uint32_t kc = (uint32_t)kk - (uint32_t)k * (G2 / 2);
+      const uint32_t rbytes = (uint32_t)(kLfHalo + (k - 1) + 128 * mt) * 16u;
+      const uint32_t v0 = 2u * kc, v1 = v0 + 1;  // virtual channel groups of [h_lft (Y_0) | h_sine (Y_1)]
+      a0 = buf0 + (v0 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v0 % G) * strip + rbytes;
+      a1h = buf0 + (v1 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v1 % G) * strip + rbytes;
+      a1l = a1h + plane;
+      b_grp = 2u * (uint32_t)p->N2 * 16u;
+      b_addr = w_base + L.off_w_out + ((uint32_t)k * G2 + v0) * b_grp;
+    }
+    p->desc[3 * e + 0] = lf_desc_lo(a0, a1h - a0);                    // a_hi
+    p->desc[3 * e + 1] = lf_desc_lo(a0 + plane, a1l - (a0 + plane));  // a_lo
+    p->desc[3 * e + 2] = lf_desc_lo(b_addr, b_grp);                   // [w_hi | w_lo]
+  }
+  return 0;
 }
 
 // small fp32 parameters in shared memory, per branch (each padded to 32 floats): c1 w tap0..2, c1 b, r1 w, r1 b,
@@ -167,53 +223,6 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
     }
     s_par[i] = v;
   }
-  // ---- UMMA descriptor table.  Every (layer, branch, M-tile, tap, K chunk) uses the same shared-memory
-  //      addresses for every work item, so the three descriptors of a chunk (a_hi, a_lo, [w_hi|w_lo]) are built
-  //      once, in issue order; the MMA thread then only streams them (its instruction rate is what bounds the
-  //      kernel otherwise: ~40 instructions of address arithmetic per chunk against a 16-cycle MMA).
-  {
-    uint2* s_desc = reinterpret_cast<uint2*>(smem + L.off_desc);
-    const uint32_t n1 = 3u * (uint32_t)(Gp / 2), G2 = 2u * (uint32_t)G, n2 = 3u * (G2 / 2);
-    const uint32_t n_chain = 6u * 2u * n1, n_all = n_chain + 2u * n2;
-    const uint32_t buf0 = smem_u32(smem + buf_off0), zero_addr = smem_u32(smem + L.off_zero), w_base = smem_u32(smem);
-    const uint32_t desc_hi = (uint32_t)(umma_desc(0, 0, 128) >> 32);
-    auto desc_lo = [](uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); };
-    for (uint32_t e = tid; e < n_all; e += kLfThreads) {
-      uint32_t a0, a1h, a1l, b_addr, b_grp;
-      if (e < n_chain) {
-        const uint32_t lb = e / (2u * n1), r = e - lb * 2u * n1;
-        const int layer = (int)(lb >> 1), br = (int)(lb & 1u);
-        const int mt = (int)(r / n1), kk = (int)(r - (uint32_t)mt * n1);
-        const int k = kk / (Gp / 2), kc = kk - k * (Gp / 2);
-        const int s0 = layer == 0 ? -6 : (layer == 1 ? -2 : -1), d = layer == 0 ? 2 : (layer == 1 ? 4 : 1);
-        const int src = layer == 1 ? 1 : 0;  // a1 / y live in X (0), a2 in Y (1)
-        const uint32_t w_addr = w_base + (layer == 0 ? L.off_w_c2[br] : (layer == 1 ? L.off_w_c4[br] : L.off_w_film[br]));
-        const uint32_t rbytes = (uint32_t)(s0 + kLfHalo - d + k * d + 128 * mt) * 16u;
-        const int g0 = 2 * kc, g1 = g0 + 1;
-        a0 = buf0 + (uint32_t)(2 * br + src) * buf_bytes + (uint32_t)g0 * strip + rbytes;
-        // second 8-channel column: the next real group, or the shared zero strip for the K padding
-        a1h = g1 < G ? a0 + strip : zero_addr + rbytes;
-        a1l = g1 < G ? a0 + plane + strip : zero_addr + rbytes;
-        b_grp = 2u * (uint32_t)p.N1 * 16u;
-        b_addr = w_addr + ((uint32_t)k * Gp + g0) * b_grp;
-      } else {
-        const uint32_t r = e - n_chain;
-        const int mt = (int)(r / n2), kk = (int)(r - (uint32_t)mt * n2);
-        const int k = kk / (int)(G2 / 2);
-        const uint32_t kc = (uint32_t)kk - (uint32_t)k * (G2 / 2);
-        const uint32_t rbytes = (uint32_t)(kLfHalo + (k - 1) + 128 * mt) * 16u;
-        const uint32_t v0 = 2u * kc, v1 = v0 + 1;  // virtual channel groups of [h_lft (Y_0) | h_sine (Y_1)]
-        a0 = buf0 + (v0 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v0 % G) * strip + rbytes;
-        a1h = buf0 + (v1 >= (uint32_t)G ? 3u : 1u) * buf_bytes + (v1 % G) * strip + rbytes;
-        a1l = a1h + plane;
-        b_grp = 2u * (uint32_t)p.N2 * 16u;
-        b_addr = w_base + L.off_w_out + ((uint32_t)k * G2 + v0) * b_grp;
-      }
-      s_desc[3 * e + 0] = make_uint2(desc_lo(a0, a1h - a0), desc_hi);                    // a_hi
-      s_desc[3 * e + 1] = make_uint2(desc_lo(a0 + plane, a1l - (a0 + plane)), desc_hi);  // a_lo
-      s_desc[3 * e + 2] = make_uint2(desc_lo(b_addr, b_grp), desc_hi);                   // [w_hi | w_lo]
-    }
-  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -223,6 +232,10 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
 
   if (warp == 12) {
     // ================= weights + MMA issuer =================
+    // The whole warp runs the warp-uniform control flow; descriptors come from the kernel parameters (constant bank
+    // -> uniform registers) plus the shared-memory base; one elected lane issues the tcgen05 instructions.  (Issued
+    // from inside `if (lane == 0)` with the descriptors read from shared memory, each chunk cost 21 instructions
+    // -- 3 LDS.64, 6 vector->uniform moves, election -- and the issuing warp was busy for the whole kernel.)
     if (lane == 0) {
       const uint32_t total = 6u * L.w1_bytes + L.w2_bytes;
       mbar_expect_tx(bar_w, total);
@@ -232,29 +245,33 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         bulk_g2s(smem + L.off_w_film[br], p.w_film[br], L.w1_bytes, bar_w);
       }
       bulk_g2s(smem + L.off_w_out, p.w_out, L.w2_bytes, bar_w);
-      mbar_wait2(bar_w, 0);
+    }
+    __syncwarp();
+    mbar_wait2(bar_w, 0);
+    {
+      const bool leader = elect_one_sync();
       const uint32_t idesc_c = umma_idesc_bf16(128, 2 * p.N1), idesc_h = umma_idesc_bf16(128, p.N1);
       const uint32_t idesc_oc = umma_idesc_bf16(128, 2 * p.N2), idesc_oh = umma_idesc_bf16(128, p.N2);
-      const uint32_t desc_base = smem_u32(smem + L.off_desc);
+      const uint32_t base4 = smem_u32(smem) >> 4;
+      const uint64_t desc_hi = umma_desc(0, 0, 128) & 0xFFFFFFFF00000000ull;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t n1 = 3u * (uint32_t)(Gp / 2), n2 = 3u * (uint32_t)G;
       uint32_t ready_phase0 = 0u, ready_phase1 = 0u;
-      auto lds64 = [](uint32_t addr) {
-        uint64_t v;
-        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
-        return v;
-      };
-      // stream the precomputed descriptors of one M-tile: a_hi x [w_hi | w_lo] -> columns [0, 2N), a_lo x w_hi -> [0, N)
-      auto issue_mtile = [&](uint32_t d_tmem, uint32_t& dp, uint32_t n_chunks, uint32_t idesc_wide, uint32_t idesc_half) {
+      // one M-tile: a_hi x [w_hi | w_lo] -> columns [0, 2N), a_lo x w_hi -> [0, N)
+      auto issue_mtile = [&](uint32_t d_tmem, uint32_t& di, uint32_t n_chunks, uint32_t idesc_wide, uint32_t idesc_half) {
         uint32_t accum = 0u;
-        for (uint32_t i = 0; i < n_chunks; ++i, dp += 24u) {
-          const uint64_t A_hi = lds64(dp), A_lo = lds64(dp + 8u), Bd = lds64(dp + 16u);
-          umma_bf16(d_tmem, A_hi, Bd, idesc_wide, accum);
-          umma_bf16(d_tmem, A_lo, Bd, idesc_half, 1u);
+        for (uint32_t i = 0; i < n_chunks; ++i, di += 3u) {
+          const uint64_t A_hi = desc_hi | (uint64_t)(p.desc[di] + base4), A_lo = desc_hi | (uint64_t)(p.desc[di + 1u] + base4);
+          const uint64_t Bd = desc_hi | (uint64_t)(p.desc[di + 2u] + base4);
+          if (leader) {
+            umma_bf16(d_tmem, A_hi, Bd, idesc_wide, accum);
+            umma_bf16(d_tmem, A_lo, Bd, idesc_half, 1u);
+          }
           accum = 1u;
         }
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        uint32_t dp = desc_base;
+        uint32_t di = 0u;
         for (int layer = 0; layer < 3; ++layer) {      // a1 (X) -> a2 (Y) -> y (X) -> h (Y), branches interleaved
           for (int br = 0; br < 2; ++br) {
             if (br == 0) {
@@ -266,8 +283,8 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
             }
             tc_fence_after();
             for (int mt = 0; mt < 2; ++mt) {
-              issue_mtile(tmem + (uint32_t)(2 * br + mt) * 64u, dp, n1, idesc_c, idesc_h);
-              umma_commit(bar_acc + 2 * br + mt);
+              issue_mtile(tmem_u + (uint32_t)(2 * br + mt) * 64u, di, n1, idesc_c, idesc_h);
+              if (leader) umma_commit(bar_acc + 2 * br + mt);
             }
           }
         }
@@ -278,10 +295,11 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         ready_phase1 ^= 1u;
         tc_fence_after();
         for (int mt = 0; mt < 2; ++mt) {
-          issue_mtile(tmem + (uint32_t)mt * 128u, dp, n2, idesc_oc, idesc_oh);
-          umma_commit(bar_acc + mt);
+          issue_mtile(tmem_u + (uint32_t)mt * 128u, di, n2, idesc_oc, idesc_oh);
+          if (leader) umma_commit(bar_acc + mt);
         }
       }
+      __syncwarp();
     }
   } else {
     // ================= workers =================
