@@ -54,12 +54,14 @@ struct Tc3Cfg {
   uint32_t off_w, off_a, off_b, off_scr, off_pa, off_fin, off_tab, off_stg, off_bar, total;
   uint32_t stg_bytes;  // one slot of the transform's raw-row staging ring (a chunk: kXW warps x CH tasks x 1 KB)
   int stg_depth;       // chunks in flight (ring of stg_depth + 1 slots)
+  int cpw;             // tasks per transform warp and chunk (<= kTc3ChunkItems): smaller chunks = smaller staging slots
 };
 
 struct Tc3Launch {
   Tc2Args a;
   long long d_in, d_w, d_bias, d_gen_w, d_gen_b, d_res, d_gres_w, d_gres_b, d_gres_x, d_raw, d_out;  // elements
   Tc3Cfg c;
+  int tl_slot;  // launch index inside the forward (event timeline builds only)
 };
 
 __device__ __forceinline__ bool elect_one_sync() {
@@ -172,6 +174,25 @@ __device__ __forceinline__ void split_store_p(uint32_t addr, uint32_t plane, con
       : "memory");
 }
 
+// ---- optional event timeline (build with -DFSVC_TIMELINE; tools/timeline.py): globaltimer stamps of the first
+// 8 CTAs of every conv_tc3 launch of a forward, to see where a short kernel's latency goes.  Compiled out otherwise.
+#ifdef FSVC_TIMELINE
+__device__ unsigned long long g_tl[64 * 8 * 64];
+__device__ __forceinline__ unsigned long long tl_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FSVC_TL(slot, ev)                                                                          \
+  do {                                                                                             \
+    if (blockIdx.x < 8 && (slot) < 64) g_tl[(((slot) * 8) + blockIdx.x) * 64 + (ev)] = tl_now();   \
+  } while (0)
+#else
+#define FSVC_TL(slot, ev) \
+  do {                    \
+  } while (0)
+#endif
+
 enum {  // mbarrier indices
   kBarBFull = 0,     // [2] streamed weight block landed
   kBarBEmpty = 2,    // [2] MMAs that read it completed
@@ -207,12 +228,16 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
   const uint32_t pa_bytes = 3u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;  // triple-buffered per-utterance affine
   // Preference: deep staging (loads in flight) first, then A ring depth.
   const uint32_t xw = small ? 2u : 6u;
-  c->stg_bytes = a.gen_w ? 0u : xw * (uint32_t)kTc3ChunkItems * 1024u;
-  static const int pref[][2] = {{3, 3}, {2, 3}, {3, 2}, {2, 2}, {3, 1}, {2, 1}, {1, 1}};  // {a_slots, stg_depth}
+  // {A ring slots, staging depth, tasks per warp and chunk}: deep staging first, then A ring depth; half-size chunks
+  // (half the staging memory) before giving up the double-buffered A ring
+  static const int pref[][3] = {{3, 3, 4}, {2, 3, 4}, {3, 2, 4}, {2, 2, 4}, {3, 1, 4}, {2, 1, 4},
+                                {3, 1, 2}, {2, 1, 2}, {1, 1, 4}, {1, 1, 2}};
   for (const auto& pr : pref) {
     const int slots = pr[0];
     c->a_slots = slots;
     c->stg_depth = a.gen_w ? 0 : pr[1];
+    c->cpw = pr[2];
+    c->stg_bytes = a.gen_w ? 0u : xw * (uint32_t)c->cpw * 1024u;
     uint32_t off = 0;
     c->off_w = off;
     off += w_bytes;
@@ -276,6 +301,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   uint32_t acc_stride = 32;
   while (acc_stride < (uint32_t)a.N_tile) acc_stride <<= 1;
 
+  if (tid == 0) FSVC_TL(L.tl_slot, 0);
   griddep_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -296,6 +322,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
+  if (tid == 0) FSVC_TL(L.tl_slot, 1);
 
   const int nvalid = min(a.N_tile, a.C_out - nt * a.N_tile);  // valid output channels of this N tile
   const int n_sub = (nvalid + c.nsub - 1) / c.nsub;           // epilogue sub-tiles of this N tile
@@ -352,6 +379,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         const uint32_t d_tmem = tmem_u + acc * acc_stride;
         for (int blk = 0; blk < a.n_blk; ++blk) {
           mbar_wait2(bars + kBarAFull + aslot, ause & 1u);
+          if (leader && it == 0 && blk < 12) FSVC_TL(L.tl_slot, 20 + blk);
           uint32_t sB_addr;
           const uint32_t bslot = pbk & 1u;
           if (a.w_resident) {
@@ -384,6 +412,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             umma_commit(bars + kBarAEmpty + aslot);
             if (!a.w_resident) umma_commit(bars + kBarBEmpty + bslot);
             if (blk == a.n_blk - 1) umma_commit(bars + kBarAccFull + acc);
+            if (it == 0 && blk == a.n_blk - 1) FSVC_TL(L.tl_slot, 36);
           }
           if (!a.w_resident) ++pbk;
           if (++aslot == (uint32_t)c.a_slots) {
@@ -595,10 +624,11 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     }
     const uint32_t s_tab = smem_u32(tab);
     // staging ring: slot = one chunk; per task 2 x 512 B (the two 4-channel halves), lane-private 16 B pieces
-    const uint32_t stg0 = smem_base + c.off_stg + (uint32_t)xw * (kTc3ChunkItems * 1024u) + (uint32_t)lane * 16u;
+    const uint32_t stg0 = smem_base + c.off_stg + (uint32_t)(xw * c.cpw) * 1024u + (uint32_t)lane * 16u;
     constexpr int CH = kTc3ChunkItems;
     const int rounds = (ntask + SH::kXW - 1) / SH::kXW;
-    const int n_chunks = (rounds + CH - 1) / CH;
+    const int cpw = c.cpw;  // tasks per warp and chunk actually used (<= CH, the unroll bound)
+    const int n_chunks = (rounds + cpw - 1) / cpw;
     const bool has_aff = a.pre_a != nullptr || a.pre_stats != nullptr;
     // statistics merge: fin_cw channels at a time, fin_P threads (segment phases) per channel
     const int fin_cw = min(a.C_in, kTc3XformThreads), fin_P = kTc3XformThreads / fin_cw;
@@ -719,12 +749,12 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         tile_rows(q, u_lo, s_first, s_last);
         const int cg0 = q.blk * Gb;
         const long long rowbase = (long long)q.b * Tp_in;
-        const int kbase = q.ch * CH * SH::kXW + xw;
+        const int kbase = q.ch * cpw * SH::kXW + xw;
         const uint32_t dst0 = stg0 + slot * c.stg_bytes;
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           const int k = kbase + j * SH::kXW;
-          if (k < ntask) {  // warp-uniform
+          if (j < cpw && k < ntask) {  // warp-uniform
             const int g = nseg == 1 ? k : (int)__umulhi((uint32_t)k, seg_magic), seg = k - g * nseg;
             const int sr = s_first + seg * 32 + lane;
             const bool ok = sr <= s_last && (cg0 + g) * 8 < a.C_in;
@@ -737,6 +767,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       cp_async_commit();
     };
     griddep_wait();  // first access to the predecessor's output
+    if (tt == 0) FSVC_TL(L.tl_slot, 2);
     uint32_t aslot = 0, ause = 0, pa_buf = 0;  // A ring position; affine buffer of the tile being converted
     const uint32_t sA0 = smem_base + c.off_a + (uint32_t)lane * 16u;
     const uint32_t s_pa0 = smem_base + c.off_pa;
@@ -766,11 +797,11 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       const uint32_t s_pa = s_pa0 + pa_buf * (uint32_t)(2 * cpad) * 4u + (uint32_t)(q.blk * Gb) * 32u;
       const uint32_t s_pc = s_pa + (uint32_t)cpad * 4u;
       const int cg0 = q.blk * Gb;
-      const int kbase = q.ch * CH * SH::kXW + xw;
+      const int kbase = q.ch * cpw * SH::kXW + xw;
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const int k = kbase + j * SH::kXW;
-        if (k < ntask) {  // warp-uniform
+        if (j < cpw && k < ntask) {  // warp-uniform
           const int g = nseg == 1 ? k : (int)__umulhi((uint32_t)k, seg_magic), seg = k - g * nseg;
           const float4 dA = lds128f(src0 + (uint32_t)j * 1024u), dB = lds128f(src0 + (uint32_t)j * 1024u + 512u);
           float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
@@ -809,6 +840,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       if (q.ch == n_chunks - 1) {
         fence_proxy_async();
         mbar_arrive(bars + kBarAFull + aslot);
+        if (tt == 0 && q.it == 0 && q.blk < 12) FSVC_TL(L.tl_slot, 4 + q.blk);
         if (++aslot == (uint32_t)c.a_slots) {
           aslot = 0;
           ++ause;
@@ -839,6 +871,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         if (depth == 3) cp_async_wait<3>();
         else if (depth == 2) cp_async_wait<2>();
         else cp_async_wait<1>();
+        if (tt == 0 && cur.it == 0 && cur.blk == 0 && cur.ch == 0) FSVC_TL(L.tl_slot, 3);
         convert_chunk(cur, slot_c);
         slot_c = slot_c + 1 == (uint32_t)depth + 1 ? 0 : slot_c + 1;
         cur = nxt;
@@ -853,12 +886,12 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         const int cg0 = q.blk * Gb;
         const long long rowbase = (long long)q.b * Tp_in;
         const float4* tb = in4 + (rowbase + t0) * ld4 + thr_goff + cg0 * 64;
-        const int kbase = q.ch * CH * SH::kXW + xw;
+        const int kbase = q.ch * cpw * SH::kXW + xw;
         const uint32_t dst0 = stg0 + slot * c.stg_bytes;
 #pragma unroll
         for (int j = 0; j < CH; ++j) {
           const int k = kbase + j * SH::kXW;
-          if (k < ntask) {  // warp-uniform
+          if (j < cpw && k < ntask) {  // warp-uniform
             const int4 e = lds128i(s_tab + (uint32_t)k * 16u);
             const int g = e.w >> 16, u = ut + (e.w & 0xffff);
             const bool ok = lane < e.z && (unsigned)u < (unsigned)a.T_out && (cg0 + g) * 8 < a.C_in;
@@ -876,6 +909,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       cp_async_commit();
     };
     griddep_wait();  // first access to the predecessor's output
+    if (tt == 0) FSVC_TL(L.tl_slot, 2);
     uint32_t aslot = 0, ause = 0, pa_buf = 0;  // A ring position; affine buffer of the tile being converted
     const uint32_t sA0 = smem_base + c.off_a + (uint32_t)lane * 16u;
     const uint32_t s_pa0 = smem_base + c.off_pa;
@@ -893,11 +927,11 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       const uint32_t sA = sA0 + aslot * c.a_bytes;
       const uint32_t s_pa = s_pa0 + pa_buf * (uint32_t)(2 * cpad) * 4u + (uint32_t)(q.blk * Gb) * 32u;
       const uint32_t s_pc = s_pa + (uint32_t)cpad * 4u;
-      const int kbase = q.ch * CH * SH::kXW + xw;
+      const int kbase = q.ch * cpw * SH::kXW + xw;
 #pragma unroll
       for (int j = 0; j < CH; ++j) {
         const int k = kbase + j * SH::kXW;
-        if (k < ntask) {  // warp-uniform
+        if (j < cpw && k < ntask) {  // warp-uniform
           const int4 e = lds128i(s_tab + (uint32_t)k * 16u);
           const float4 dA = lds128f(src0 + (uint32_t)j * 1024u), dB = lds128f(src0 + (uint32_t)j * 1024u + 512u);
           float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
@@ -923,6 +957,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       if (q.ch == n_chunks - 1) {
         fence_proxy_async();
         mbar_arrive(bars + kBarAFull + aslot);
+        if (tt == 0 && q.it == 0 && q.blk < 12) FSVC_TL(L.tl_slot, 4 + q.blk);
         if (++aslot == (uint32_t)c.a_slots) {
           aslot = 0;
           ++ause;
@@ -953,6 +988,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         if (depth == 3) cp_async_wait<3>();
         else if (depth == 2) cp_async_wait<2>();
         else cp_async_wait<1>();
+        if (tt == 0 && cur.it == 0 && cur.blk == 0 && cur.ch == 0) FSVC_TL(L.tl_slot, 3);
         convert_chunk(cur, slot_c);
         slot_c = slot_c + 1 == (uint32_t)depth + 1 ? 0 : slot_c + 1;
         cur = nxt;
@@ -1011,6 +1047,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       }
     };
     griddep_wait();  // before the first operand load and the first store
+    if (ew == 0 && lane == 0) FSVC_TL(L.tl_slot, 37);
     int b = first / c.m_tiles, tile = first - b * c.m_tiles;
     if (first < n_m) load_ops(b, tile, 0);
     int it = 0;
@@ -1030,6 +1067,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       float* out_row = out ? out + ntc_row(Tp_out, a.out_ld, b, t) : nullptr;
       float2* st_row = has_stats ? a.stats + ((long long)b * a.n_seg + (t0 >> 5) + q) * a.C_out : nullptr;
       mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
+      if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 38);
       tc_fence_after();
       const uint32_t tacc = tmem + acc * acc_stride + lane_addr;
       for (int sub = 0; sub < n_sub; ++sub) {
@@ -1130,12 +1168,14 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       }
       tc_fence_before();
       mbar_arrive(bars + kBarAccEmpty + acc);
+      if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 39);
       b = nb;
       tile = ntile;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) FSVC_TL(L.tl_slot, 40);
   if (warp == SH::kMmaWarp) {
     __syncwarp();
     tmem_dealloc(tmem, 2 * acc_stride);

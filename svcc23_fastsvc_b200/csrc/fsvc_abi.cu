@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -719,6 +720,7 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
       return;
     }
   }
+  L.tl_slot = c.launches;
   Tc3Cfg& cfg = L.c;
   cfg.n_prob = n_prob;
   cfg.B = c.B;
@@ -737,6 +739,11 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   per_group = per_group < 1 ? 1 : per_group;
   per_group = per_group > items ? items : per_group;
   const dim3 grid(per_group * groups);
+  if (c.prof && getenv("FSVC_DEBUG_PLAN"))
+    fprintf(stderr, "plan %-4s %-12s Cin=%d Cout=%d K=%d dil=%d up=%d down=%d CIB=%d n_blk=%d N_tile=%d n_ntiles=%d resident=%d "
+                    "a_slots=%d stg_depth=%d smem=%u grid=%u items=%d\n",
+            c.label, name, p[0].C_in, p[0].C_out, K, p[0].dil, p[0].up, p[0].down, p[0].CIB, p[0].n_blk, p[0].N_tile,
+            p[0].n_ntiles, p[0].w_resident, cfg.a_slots, cfg.stg_depth, cfg.total, grid.x, items);
   // compile-time epilogue width (12 channels per thread) when every sub-tile of every N tile is full
   const int per_thread = cfg.nsub / (small ? 1 : 2);
   const bool nh3 = per_thread == 12 && p[0].C_out % cfg.nsub == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % cfg.nsub == 0);
@@ -1571,6 +1578,14 @@ int fsvc_pcm16(const float* x, int16_t* y, long long n, void* stream) {
   FSVC_CUDA(cudaGetLastError());
   return FSVC_OK;
 }
+
+#ifdef FSVC_TIMELINE
+// debug builds only (tools/timeline.py): copy the event stamps of the last forward
+int fsvc_debug_timeline(unsigned long long* out, int n) {
+  FSVC_CUDA(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * (size_t)(n < 64 * 8 * 64 ? n : 64 * 8 * 64)));
+  return FSVC_OK;
+}
+#endif
 
 int fsvc_last_launch_count(const fsvc_handle* h) { return h ? h->launches : FSVC_E_INVALID; }
 
