@@ -205,7 +205,7 @@ enum {  // mbarrier indices
 };
 
 // Shared-memory plan of one launch.  Returns false when even a 1-deep A ring does not fit.
-__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool small = false) {
+__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool small = false, int cpw_force = 0) {
   const int halo = (K / 2) * a.dil, W = kTc2M + 2 * halo;
   const uint32_t Gb = a.CIB / 8;
   c->a_bytes = 2u * Gb * W * 16u;
@@ -236,7 +236,8 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
     const int slots = pr[0];
     c->a_slots = slots;
     c->stg_depth = a.gen_w ? 0 : pr[1];
-    c->cpw = pr[2];
+    c->cpw = cpw_force ? cpw_force : pr[2];
+    if (cpw_force && pr[2] != 4) continue;
     c->stg_bytes = a.gen_w ? 0u : xw * (uint32_t)c->cpw * 1024u;
     uint32_t off = 0;
     c->off_w = off;
@@ -733,7 +734,134 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         }
       }
     };
-   if constexpr (MODE == 2) {
+   if constexpr (MODE >= 3) {
+    // ---- MODE 3 / 4: the lean transform of the many-tile layers (up == down == 1, one ci block, every warp's tasks of
+    // an item in ONE chunk of at most NT).  Profiling the table-driven loop showed 726 instructions per item and warp for
+    // three tasks at 0.2 IPC -- the role that paces every such layer -- most of them geometry, predicates and branches.
+    // Here everything tile-invariant (global / shared offsets, window membership, affine row) is computed once into
+    // registers; per item a task costs its address add, one bounds compare, two copies / two loads, the arithmetic
+    // and two predicated stores.
+    constexpr int NT = MODE == 4 ? 6 : 4;
+    int goff[NT], rel[NT];
+    uint32_t soff[NT], aoff[NT], flags[NT];  // flags: bit 0 = task exists, bit 1 = this lane's row is inside the window
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int k = xw + j * SH::kXW;
+      const int g = k / nseg, seg = k - g * nseg;
+      const bool on = k < ntask && g * 8 < a.C_in;  // (channel padding groups are zero-filled once, below)
+      goff[j] = (int)(seg * 32 * ld4) + g * 64;
+      rel[j] = seg * 32 + hl;
+      soff[j] = (uint32_t)g * strip + (uint32_t)seg * 512u + (uint32_t)lane * 16u;
+      aoff[j] = (uint32_t)g * 32u;
+      flags[j] = (on ? 1u : 0u) | ((on && seg * 32 + lane < W) ? 2u : 0u);
+    }
+    // channel-padding groups of the (single) ci block never change: zero them in every A slot once
+    for (int sl = 0; sl < c.a_slots; ++sl)
+      for (int idx = tt; idx < Gb * W; idx += kTc3XformThreads) {
+        const int g = idx / W, rw = idx - g * W;
+        if (g * 8 >= a.C_in) {
+          const uint32_t d = smem_base + c.off_a + (uint32_t)sl * c.a_bytes + (uint32_t)g * strip + (uint32_t)rw * 16u;
+          sts128(d, make_uint4(0u, 0u, 0u, 0u));
+          sts128(d + plane, make_uint4(0u, 0u, 0u, 0u));
+        }
+      }
+    const int depth = c.stg_depth;
+    const uint32_t sA0 = smem_base + c.off_a, s_pa0 = smem_base + c.off_pa;
+    const uint32_t pa_stride = (uint32_t)(2 * cpad) * 4u, pc_off = (uint32_t)cpad * 4u;
+    griddep_wait();  // first access to the predecessor's output
+    if (tt == 0) FSVC_TL(L.tl_slot, 2);
+    // item cursors: `a*` = item whose copies are issued next, `c*` = item converted next
+    int am = first, ab = first / c.m_tiles, atile = first - ab * c.m_tiles;
+    int cm = first, cb = ab, ctile = atile, it = 0;
+    uint32_t slot_i = 0, slot_c = 0, aslot = 0, ause = 0, pa_buf = 0;
+    auto issue = [&]() {
+      if (am < n_m) {
+        const int t0 = atile * kTc2M;
+        const float4* tb = in4 + ((long long)ab * Tp_in + t0) * ld4 + thr_goff;
+        const uint32_t dst0 = stg0 + slot_i * c.stg_bytes;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (flags[j] & 1u) {  // warp-uniform, loop-invariant
+            const bool ok = (flags[j] & 2u) && (unsigned)(t0 + rel[j]) < (unsigned)a.T_out;
+            const float4* p = ok ? tb + goff[j] : in4;
+            cp_async16(dst0 + (uint32_t)j * 1024u, p, ok ? 16u : 0u);
+            cp_async16(dst0 + (uint32_t)j * 1024u + 512u, p + (ok ? 32 : 0), ok ? 16u : 0u);
+          }
+        }
+        ++am;
+        if (++atile == c.m_tiles) {
+          atile = 0;
+          ++ab;
+        }
+      }
+      cp_async_commit();
+      slot_i = slot_i == (uint32_t)depth ? 0u : slot_i + 1u;
+    };
+    for (int i = 0; i < depth; ++i) issue();
+    if (cm < n_m) update_affine(Cursor{cm, 0, 0, 0, cb, ctile});
+    while (cm < n_m) {
+      // affine of the next item's utterance, one item ahead (as in the other modes)
+      int nb = cb, ntile = ctile + 1;
+      if (ntile == c.m_tiles) {
+        ntile = 0;
+        ++nb;
+      }
+      if (cm + 1 < n_m) update_affine(Cursor{cm + 1, 0, 0, it + 1, nb, ntile});
+      if (depth == 3) cp_async_wait<2>();
+      else if (depth == 2) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      if (tt == 0 && it == 0) FSVC_TL(L.tl_slot, 3);
+      if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
+      if (has_aff && cb != cv_b) {  // new utterance: its affine was written one item ago
+        cv_b = cb;
+        pa_buf = pa_buf == 2 ? 0 : pa_buf + 1;
+        named_bar_sync(1, kTc3XformThreads);
+      }
+      {
+        const uint32_t sA = sA0 + aslot * c.a_bytes;
+        const uint32_t s_pa = s_pa0 + pa_buf * pa_stride, s_pc = s_pa + pc_off;
+        const uint32_t src0 = stg0 + slot_c * c.stg_bytes;
+        const int t0 = ctile * kTc2M;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (flags[j] & 1u) {
+            const float4 dA = lds128f(src0 + (uint32_t)j * 1024u), dB = lds128f(src0 + (uint32_t)j * 1024u + 512u);
+            float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
+            if (has_aff) {
+              const float4 a0 = lds128f(s_pa + aoff[j]), a1 = lds128f(s_pa + aoff[j] + 16u);
+              const float4 c0 = lds128f(s_pc + aoff[j]), c1 = lds128f(s_pc + aoff[j] + 16u);
+              v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
+              v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
+              v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
+              v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+            }
+            if (a.pre_lrelu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
+            }
+            // rows outside the utterance are zero AFTER the prologue
+            const uint32_t in_strip = (flags[j] >> 1) & 1u;
+            const uint32_t real = (unsigned)(t0 + rel[j]) < (unsigned)a.T_out ? 1u : 0u;
+            split_store_p(sA + soff[j], plane, v, in_strip & real, in_strip & ~real);
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + kBarAFull + aslot);
+      if (tt == 0 && it < 12) FSVC_TL(L.tl_slot, 4 + it);
+      if (++aslot == (uint32_t)c.a_slots) {
+        aslot = 0;
+        ++ause;
+      }
+      slot_c = slot_c == (uint32_t)depth ? 0u : slot_c + 1u;
+      issue();
+      ++cm;
+      ++it;
+      cb = nb;
+      ctile = ntile;
+    }
+    cp_async_wait<0>();
+   } else if constexpr (MODE == 2) {
     // ---- MODE 2: nearest-repeat input.  Window row rw <-> output-rate step u = u_lo + rw reads source row u / up,
     // so a source row s feeds the window rows of steps s*up .. s*up+up-1: load + convert it once, store it `up`
     // times.  Rows of the window outside [0, T_out) (first / last tile of an utterance) are zero-filled first.

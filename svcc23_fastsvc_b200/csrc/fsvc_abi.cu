@@ -457,7 +457,9 @@ static int tc_setup_kernels() {
 #define FSVC_ATTR(K_, NH_, SM_)                                                                                         \
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
   FSVC_ATTR(3, 3, false);
   FSVC_ATTR(3, 0, false);
   FSVC_ATTR(1, 3, false);
@@ -731,7 +733,15 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   // (measured: two 224-thread CTAs per SM are no faster than one 512-thread CTA on any layer -- kept as a template
   //  option of the kernel, not instantiated)
   const bool small = false;
-  if (!small && !tc3_plan_smem(p[0], K, &cfg, false)) {
+  // transform variant: 3 / 4 = lean path (direct rows, one ci block, a warp's <= 4 / <= 6 tasks of an item in one chunk)
+  int mode = p[0].gen_w ? 1 : (p[0].up > 1 ? 2 : 0);
+  if (mode == 0 && p[0].down == 1 && p[0].n_blk == 1 && !getenv("FSVC_NO_LEAN")) {
+    const int ntask = (p[0].CIB / 8) * ((kTc2M + 2 * (K / 2) * p[0].dil + 31) / 32);
+    const int rounds = (ntask + 5) / 6;
+    if (rounds <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4)) mode = 3;
+    else if (rounds <= 6 && tc3_plan_smem(p[0], K, &cfg, false, 6) && cfg.a_slots >= 2) mode = 4;
+  }
+  if (mode < 3 && !tc3_plan_smem(p[0], K, &cfg, false)) {
     c.err = 1;
     return;
   }
@@ -748,11 +758,13 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   const int per_thread = cfg.nsub / (small ? 1 : 2);
   const bool nh3 = per_thread == 12 && p[0].C_out % cfg.nsub == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % cfg.nsub == 0);
   const int threads = small ? kTc3ThreadsSmall : kTc3Threads;
-#define FSVC_TC3(K_, NH_, SM_)                                                                              \
-  do {                                                                                                     \
-    if (p[0].gen_w) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 1>, grid, threads, cfg.total, c.stream, L);    \
-    else if (p[0].up > 1) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 2>, grid, threads, cfg.total, c.stream, L); \
-    else launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 0>, grid, threads, cfg.total, c.stream, L);               \
+#define FSVC_TC3(K_, NH_, SM_)                                                                               \
+  do {                                                                                                      \
+    if (mode == 1) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 1>, grid, threads, cfg.total, c.stream, L);      \
+    else if (mode == 2) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 2>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 3) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 3>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 4) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 4>, grid, threads, cfg.total, c.stream, L); \
+    else launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 0>, grid, threads, cfg.total, c.stream, L);                \
   } while (0)
   if (K == 3) {
     if (nh3) FSVC_TC3(3, 3, false); else FSVC_TC3(3, 0, false);
