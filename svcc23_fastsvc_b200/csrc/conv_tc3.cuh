@@ -604,7 +604,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     const int Gb = a.CIB >> 3;  // groups of 8 channels per (padded) ci block
     const uint32_t strip = (uint32_t)W * 16u, plane = (uint32_t)Gb * strip;
     // MODE 2: segments of source rows (at most ceil(W / up) + 1 of them touch a window)
-    const int nseg = MODE == 2 ? ((W + a.up - 1) / a.up + 1 + 31) >> 5 : (W + 31) >> 5, ntask = Gb * nseg;
+    const int nseg = (MODE == 2 || MODE == 5) ? ((W + a.up - 1) / a.up + 1 + 31) >> 5 : (W + 31) >> 5, ntask = Gb * nseg;
     const long long Tp_in = ntc_tp(a.T_in);
     const long long ld4 = a.in_ld >> 2;
     const uint32_t up_magic = 0xFFFFFFFFu / (uint32_t)a.up + 1u;
@@ -734,7 +734,153 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         }
       }
     };
-   if constexpr (MODE >= 3) {
+   if constexpr (MODE == 5) {
+    // ---- MODE 5: lean nearest-repeat transform (up > 1, down == 1, one ci block, <= 4 tasks per warp and item):
+    // MODE 2's arithmetic with the tile-invariant part of the geometry in registers.  A task = (8-channel group,
+    // 32 SOURCE rows); source row sr feeds window rows sr*up - u_lo .. + up - 1.
+    constexpr int NT = 4;
+    int rl[NT];
+    uint32_t gstrip[NT], gcol[NT], aoff[NT], on[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int k = xw + j * SH::kXW;
+      const int g = k / nseg, seg = k - g * nseg;
+      on[j] = (k < ntask && g * 8 < a.C_in) ? 1u : 0u;
+      rl[j] = seg * 32 + lane;
+      gstrip[j] = (uint32_t)g * strip;
+      gcol[j] = (uint32_t)g * 64u;
+      aoff[j] = (uint32_t)g * 32u;
+    }
+    for (int sl = 0; sl < c.a_slots; ++sl)  // channel-padding groups: zero once in every A slot
+      for (int idx = tt; idx < Gb * W; idx += kTc3XformThreads) {
+        const int g = idx / W, rw = idx - g * W;
+        if (g * 8 >= a.C_in) {
+          const uint32_t d = smem_base + c.off_a + (uint32_t)sl * c.a_bytes + (uint32_t)g * strip + (uint32_t)rw * 16u;
+          sts128(d, make_uint4(0u, 0u, 0u, 0u));
+          sts128(d + plane, make_uint4(0u, 0u, 0u, 0u));
+        }
+      }
+    const int depth = c.stg_depth, up = a.up;
+    const uint32_t sA0 = smem_base + c.off_a, s_pa0 = smem_base + c.off_pa;
+    const uint32_t pa_stride = (uint32_t)(2 * cpad) * 4u, pc_off = (uint32_t)cpad * 4u;
+    griddep_wait();  // first access to the predecessor's output
+    if (tt == 0) FSVC_TL(L.tl_slot, 2);
+    int am = first, ab = first / c.m_tiles, atile = first - ab * c.m_tiles;
+    int cm = first, cb = ab, ctile = atile, it = 0;
+    uint32_t slot_i = 0, slot_c = 0, aslot = 0, ause = 0, pa_buf = 0;
+    auto issue = [&]() {
+      if (am < n_m) {
+        const int u_lo = atile * kTc2M - halo;
+        const int s_first = (int)__umulhi((uint32_t)max(u_lo, 0), up_magic);
+        const int s_last = (int)__umulhi((uint32_t)min(u_lo + W - 1, a.T_out - 1), up_magic);
+        const long long rowbase = (long long)ab * Tp_in;
+        const uint32_t dst0 = stg0 + slot_i * c.stg_bytes;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (on[j]) {  // warp-uniform, loop-invariant
+            const int sr = s_first + rl[j];
+            const bool ok = sr <= s_last;
+            const float4* p = ok ? in4 + (rowbase + (sr & ~31)) * ld4 + ((uint32_t)(sr & 31) + gcol[j]) : in4;
+            cp_async16(dst0 + (uint32_t)j * 1024u, p, ok ? 16u : 0u);
+            cp_async16(dst0 + (uint32_t)j * 1024u + 512u, p + (ok ? 32 : 0), ok ? 16u : 0u);
+          }
+        }
+        ++am;
+        if (++atile == c.m_tiles) {
+          atile = 0;
+          ++ab;
+        }
+      }
+      cp_async_commit();
+      slot_i = slot_i == (uint32_t)depth ? 0u : slot_i + 1u;
+    };
+    for (int i = 0; i < depth; ++i) issue();
+    if (cm < n_m) update_affine(Cursor{cm, 0, 0, 0, cb, ctile});
+    while (cm < n_m) {
+      int nb = cb, ntile = ctile + 1;
+      if (ntile == c.m_tiles) {
+        ntile = 0;
+        ++nb;
+      }
+      if (cm + 1 < n_m) update_affine(Cursor{cm + 1, 0, 0, it + 1, nb, ntile});
+      if (depth == 3) cp_async_wait<2>();
+      else if (depth == 2) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      if (tt == 0 && it == 0) FSVC_TL(L.tl_slot, 3);
+      if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
+      if (has_aff && cb != cv_b) {  // new utterance: its affine was written one item ago
+        cv_b = cb;
+        pa_buf = pa_buf == 2 ? 0 : pa_buf + 1;
+        named_bar_sync(1, kTc3XformThreads);
+      }
+      {
+        const uint32_t sA = sA0 + aslot * c.a_bytes;
+        const uint32_t s_pa = s_pa0 + pa_buf * pa_stride, s_pc = s_pa + pc_off;
+        const uint32_t src0 = stg0 + slot_c * c.stg_bytes;
+        const int u_lo = ctile * kTc2M - halo;
+        const int s_first = (int)__umulhi((uint32_t)max(u_lo, 0), up_magic);
+        const int s_last = (int)__umulhi((uint32_t)min(u_lo + W - 1, a.T_out - 1), up_magic);
+        const uint32_t rw_end = (uint32_t)min(W, a.T_out - u_lo);
+        if (u_lo < 0 || u_lo + W > a.T_out) {  // zero padding rows of the window (first / last tile of an utterance)
+          for (int idx = tt; idx < Gb * W; idx += kTc3XformThreads) {
+            const int g = idx / W, rw = idx - g * W, u = u_lo + rw;
+            if (u < 0 || u >= a.T_out) {
+              sts128(sA + (uint32_t)g * strip + (uint32_t)rw * 16u, make_uint4(0u, 0u, 0u, 0u));
+              sts128(sA + plane + (uint32_t)g * strip + (uint32_t)rw * 16u, make_uint4(0u, 0u, 0u, 0u));
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          if (on[j]) {
+            const float4 dA = lds128f(src0 + (uint32_t)j * 1024u), dB = lds128f(src0 + (uint32_t)j * 1024u + 512u);
+            float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
+            if (has_aff) {
+              const float4 a0 = lds128f(s_pa + aoff[j]), a1 = lds128f(s_pa + aoff[j] + 16u);
+              const float4 c0 = lds128f(s_pc + aoff[j]), c1 = lds128f(s_pc + aoff[j] + 16u);
+              v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
+              v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
+              v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
+              v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+            }
+            if (a.pre_lrelu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
+            }
+            uint4 hi, lo;
+            split_bf16(v, hi, lo);
+            const int sr = s_first + rl[j];
+            const int rw0 = sr * up - u_lo;  // window row of the first step this source row feeds (may be < 0)
+            const uint32_t dst = sA + gstrip[j];
+            if (sr <= s_last) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t rw = (uint32_t)(rw0 + i);
+                if (i < up && rw < rw_end) {  // unsigned compare: negative rows fail it too
+                  sts128(dst + rw * 16u, hi);
+                  sts128(dst + plane + rw * 16u, lo);
+                }
+              }
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + kBarAFull + aslot);
+      if (tt == 0 && it < 12) FSVC_TL(L.tl_slot, 4 + it);
+      if (++aslot == (uint32_t)c.a_slots) {
+        aslot = 0;
+        ++ause;
+      }
+      slot_c = slot_c == (uint32_t)depth ? 0u : slot_c + 1u;
+      issue();
+      ++cm;
+      ++it;
+      cb = nb;
+      ctile = ntile;
+    }
+    cp_async_wait<0>();
+   } else if constexpr (MODE >= 3) {
     // ---- MODE 3 / 4: the lean transform of the many-tile layers (up == down == 1, one ci block, every warp's tasks of
     // an item in ONE chunk of at most NT).  Profiling the table-driven loop showed 726 instructions per item and warp for
     // three tasks at 0.2 IPC -- the role that paces every such layer -- most of them geometry, predicates and branches.

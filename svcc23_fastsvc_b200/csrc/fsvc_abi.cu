@@ -459,7 +459,8 @@ static int tc_setup_kernels() {
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
   FSVC_ATTR(3, 3, false);
   FSVC_ATTR(3, 0, false);
   FSVC_ATTR(1, 3, false);
@@ -741,6 +742,11 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     if (rounds <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4)) mode = 3;
     else if (rounds <= 6 && tc3_plan_smem(p[0], K, &cfg, false, 6) && cfg.a_slots >= 2) mode = 4;
   }
+  if (mode == 2 && p[0].down == 1 && p[0].up <= 8 && p[0].n_blk == 1 && !getenv("FSVC_NO_LEAN")) {
+    const int Wd = kTc2M + 2 * (K / 2) * p[0].dil;
+    const int ntask = (p[0].CIB / 8) * (((Wd + p[0].up - 1) / p[0].up + 1 + 31) / 32);
+    if ((ntask + 5) / 6 <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4)) mode = 5;
+  }
   if (mode < 3 && !tc3_plan_smem(p[0], K, &cfg, false)) {
     c.err = 1;
     return;
@@ -764,6 +770,7 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     else if (mode == 2) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 2>, grid, threads, cfg.total, c.stream, L); \
     else if (mode == 3) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 3>, grid, threads, cfg.total, c.stream, L); \
     else if (mode == 4) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 4>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 5) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 5>, grid, threads, cfg.total, c.stream, L); \
     else launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 0>, grid, threads, cfg.total, c.stream, L);                \
   } while (0)
   if (K == 3) {
