@@ -163,6 +163,11 @@ struct fsvc_handle {
   bool weights_set = false;
   int launches = 0;
   int device = 0;
+  // fsvc_forward_host only: the PPG upload runs on a side stream while the conditioning levels (which need only the
+  // two signals) compute; the forward waits for `ppg_ready` right before it first reads the PPG tensor
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_ppg = nullptr;
+  cudaEvent_t ppg_ready = nullptr;  // set for the duration of one fsvc_forward_host call
 };
 
 namespace fsvc {
@@ -531,6 +536,7 @@ static int forward_fp32(fsvc_handle* h, const float* ppg, const float* sine, con
   c.eps = h->cfg.in_eps;
   c.prof = prof;
   c.tc = mode_uses_tc(mode);
+  if (h->ppg_ready) cudaStreamWaitEvent(stream, h->ppg_ready, 0);  // fsvc_forward_host: PPG upload on the side stream
   if (prof) prof->mark(stream);
   const int n = h->n;
   const int T = frames * h->hop;
@@ -938,6 +944,7 @@ static int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, cons
 
   // ---- upsampling stages (fastsvc.py:80-140) ----
   {  // the caller's (B, C, T') PPG tensor -> channels-last
+    if (h->ppg_ready) cudaStreamWaitEvent(stream, h->ppg_ready, 0);  // fsvc_forward_host: upload on the side stream
     const int Cin = h->cfg.in_channels;
     nct_to_ntc_kernel<<<dim3((frames + 31) / 32, (Cin + 31) / 32, B), 256, 0, stream>>>(ppg, Cin, frames, ws.xin);
     c.label = "";
@@ -1240,6 +1247,12 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
     delete h;
     return rc;
   }
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_ppg, cudaEventDisableTiming) != cudaSuccess) {
+    fsvc_destroy(h);
+    return fail(FSVC_E_CUDA, "cannot create the upload stream / events");
+  }
   *out = h;
   return FSVC_OK;
 }
@@ -1248,6 +1261,9 @@ void fsvc_destroy(fsvc_handle* h) {
   if (!h) return;
   if (h->store) cudaFree(h->store);
   if (h->tc_store) cudaFree(h->tc_store);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_ppg) cudaEventDestroy(h->ev_ppg);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
 }
 
@@ -1427,13 +1443,25 @@ int fsvc_forward_host(fsvc_handle* h, const float* ppg_host, const float* sine_h
   float* d_lft = ar.get<float>(n_sig);
   float* d_spk = ar.get<float>(n_spk);
   float* d_out = ar.get<float>(n_out);
-  FSVC_CUDA(cudaMemcpyAsync(d_ppg, ppg_host, n_ppg * 4, cudaMemcpyHostToDevice, s));
+  // The two signals (and the speaker vectors) go first on the caller's stream: the conditioning levels need only them.
+  // The PPG tensor follows on the side stream -- after the signals on the copy engine, concurrently with the levels --
+  // and the forward waits for it where it first reads it (stage 0).  The side stream starts after everything already
+  // queued on the caller's stream, so the staging buffers of a previous call are never overwritten early.
   FSVC_CUDA(cudaMemcpyAsync(d_sine, sine_host, n_sig * 4, cudaMemcpyHostToDevice, s));
   FSVC_CUDA(cudaMemcpyAsync(d_lft, lft_host, n_sig * 4, cudaMemcpyHostToDevice, s));
   if (spk_host) FSVC_CUDA(cudaMemcpyAsync(d_spk, spk_host, n_spk * 4, cudaMemcpyHostToDevice, s));
+  FSVC_CUDA(cudaEventRecord(h->ev_fork, s));
+  FSVC_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_fork, 0));
+  FSVC_CUDA(cudaMemcpyAsync(d_ppg, ppg_host, n_ppg * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  FSVC_CUDA(cudaEventRecord(h->ev_ppg, h->copy_stream));
+  h->ppg_ready = h->ev_ppg;
   rc = fsvc_forward(h, d_ppg, d_sine, d_lft, spk_host ? d_spk : nullptr, d_out, B, frames, (char*)workspace + ar.off,
                     workspace_bytes - ar.off, mode, stream_);
-  if (rc) return rc;
+  h->ppg_ready = nullptr;
+  if (rc) {
+    cudaStreamWaitEvent(s, h->ev_ppg, 0);  // rejoin the side stream even when the forward was not enqueued
+    return rc;
+  }
   FSVC_CUDA(cudaMemcpyAsync(out_host, d_out, n_out * 4, cudaMemcpyDeviceToHost, s));
   return FSVC_OK;
 }
