@@ -1043,7 +1043,6 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     griddep_wait();  // first access to the predecessor's output
     if (tt == 0) FSVC_TL(L.tl_slot, 2);
     uint32_t aslot = 0, ause = 0, pa_buf = 0;  // A ring position; affine buffer of the tile being converted
-    const uint32_t sA0 = smem_base + c.off_a + (uint32_t)lane * 16u;
     const uint32_t s_pa0 = smem_base + c.off_pa;
     auto convert_chunk = [&](const Cursor& q, uint32_t slot) {
       const uint32_t src0 = stg0 + slot * c.stg_bytes;
