@@ -86,7 +86,11 @@ class _GeneratorFn(torch.autograd.Function):
         x, s, l = saved[:3]
         spk = saved[3] if ctx.has_spk else None
         params = [p for p in g.parameters()]
-        with torch.enable_grad():
+        # full fp32 in the interim graph: with cuDNN's default TF32 convolutions the parameter gradients drift ~2 %
+        # from the reference's fp32 CPU autograd (tests/test_grads.py)
+        with torch.enable_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
+                                                             deterministic=torch.backends.cudnn.deterministic,
+                                                             allow_tf32=False):
             ins = [t.detach().requires_grad_(need) for t, need in zip((x, s, l), ctx.needs_input_grad[1:4])]
             spk_in = None
             if spk is not None:
