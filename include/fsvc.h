@@ -167,8 +167,9 @@ int fsvc_sine_excitation(const float* f0, const float* noise, float* out, int B,
                          float sample_rate, float sine_amp, float noise_amp, void* stream);
 
 /*
- * Waveform -> PCM-16 as soundfile.write(..., "PCM_16") stores it (decode_fastsvc.py:193-198): lrintf(x * 32767),
- * saturating. x, y: device pointers to n samples.
+ * Waveform -> PCM-16 as soundfile.write(..., "PCM_16") stores it (decode_fastsvc.py:193-198): libsndfile's clipping
+ * float->short conversion (soundfile always enables SFC_SET_CLIPPING): top 16 bits of lrintf(x * 2^31), saturating,
+ * i.e. floor(x * 32768) clipped to [-32768, 32767]. x, y: device pointers to n samples.
  */
 int fsvc_pcm16(const float* x, int16_t* y, long long n, void* stream);
 

@@ -47,3 +47,17 @@ def f0_convert(f0, org_stats, trg_stats):
     nz = f0 > 0
     out[nz] = np.exp((trg_stats[1] / org_stats[1]) * (np.log(f0[nz]) - org_stats[0]) + trg_stats[0])
     return out
+
+
+def pcm16(x):
+    """float waveform -> int16 as ``soundfile.write(..., "PCM_16")`` stores it (decode_fastsvc.py:193-198).
+
+    soundfile (python-soundfile, absent from this image; the reference pins none) opens files with
+    SFC_SET_CLIPPING enabled, so libsndfile converts with ``f2les_clip_array`` (src/pcm.c, published algorithm):
+    ``scaled = x * 2^31`` in float; ``>= (float)0x7FFFFFFF`` -> 0x7FFF; ``<= -2^31`` -> -0x8000; otherwise the top 16
+    bits of ``lrintf(scaled)``.  Parity unpinned: restated from the library's source, not checked against it here."""
+    x = np.asarray(x, dtype=np.float32)
+    v = x * np.float32(2147483648.0)
+    q = np.rint(np.clip(v, -2147483648.0, 2147483520.0).astype(np.float64)).astype(np.int64) >> 16
+    q = np.where(v >= np.float32(2147483648.0), 0x7FFF, np.where(v <= np.float32(-2147483648.0), -0x8000, q))
+    return q.astype(np.int16)

@@ -103,16 +103,21 @@ __global__ void __launch_bounds__(kExcThreads) sine_excitation_kernel(const ExcA
   }
 }
 
-// float waveform -> PCM-16 as soundfile.write(..., "PCM_16") stores it (decode_fastsvc.py:193-198): libsndfile's
-// f2s_array, lrintf(x * 32767) (round to nearest even).  Out-of-range samples saturate here (libsndfile without
-// SFC_SET_CLIPPING wraps them) -- the only deliberate difference, and only for |x| > 1.
+// float waveform -> PCM-16 as soundfile.write(..., "PCM_16") stores it (decode_fastsvc.py:193-198).  python-soundfile
+// opens every file with SFC_SET_CLIPPING on, so libsndfile (third-party, not in /root/reference; 1.0.x/1.2.x src/pcm.c)
+// converts with f2les_clip_array: scaled = x * 2^31 (float), saturate at >= 0x7FFFFFFF / <= -2^31, lrintf, keep the
+// top 16 bits -- i.e. floor(x * 32768) with clipping, NOT rint(x * 32767).  Restated here from the published
+// algorithm; neither libsndfile nor soundfile is installed in this image, so this step is "parity unpinned".
 __global__ void __launch_bounds__(256) pcm16_kernel(const float* __restrict__ x, int16_t* __restrict__ y, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long j = i; j < n; j += stride) {
-    float v = __fmul_rn(x[j], 32767.0f);
-    v = fminf(fmaxf(v, -32768.0f), 32767.0f);
-    y[j] = (int16_t)__float2int_rn(v);
+    const float v = __fmul_rn(x[j], 2147483648.0f);
+    int q;
+    if (v >= 2147483648.0f) q = 0x7FFF;           // (float)0x7FFFFFFF == 2^31
+    else if (v <= -2147483648.0f) q = -0x8000;
+    else q = __float2int_rn(v) >> 16;             // arithmetic shift: the top 16 bits of the 32-bit sample
+    y[j] = (int16_t)q;
   }
 }
 

@@ -3,8 +3,10 @@
 ``SignalGenerator`` keeps the reference's constructor, ``signal_types`` semantics and call signature
 (``gen(f0) -> (B, n_types, T)``).  ``sinusoid`` runs the batched CUDA kernel ``fsvc_sine_excitation``; its Gaussian
 noise is drawn with ``torch.randn`` on the input's device exactly where the reference draws it (features.py:194), so a
-seeded run consumes the RNG stream the same way.  CUDA tensors only: there is no CPU fallback (the CPU restatement
-is the test oracle, oracle/features_numpy.py).  ``F0Statistics`` is host-side numpy, as in the reference.
+seeded run consumes the RNG stream the same way.  HOST tensors take the reference's own torch ops: that is the
+data-pipeline use (the reference's ``Collater`` builds the excitation on the CPU inside DataLoader worker
+processes, train_fastsvc.py:546), which north_star leaves in PyTorch; a CUDA tensor never falls back to it.
+``F0Statistics`` is host-side numpy, as in the reference.
 """
 import logging
 import sys
@@ -77,10 +79,11 @@ class SignalGenerator:
     @torch.no_grad()
     def sinusoid(self, f0, noise=None):
         """f0 (B, 1, T') -> NSF sine excitation (B, 1, T'*hop).  ``noise`` overrides the torch.randn draw (tests)."""
-        _require_cuda(f0, "SignalGenerator.sinusoid")
         if f0.dim() != 3 or f0.size(1) != 1:
             raise ValueError(f"f0 must be (B, 1, T'), got {tuple(f0.shape)}")
         B, _, T = f0.size()
+        if not f0.is_cuda:
+            return self._sinusoid_host(f0, noise)
         f0c = f0.to(torch.float32).contiguous()
         out = torch.empty((B, 1, T * self.hop_size), dtype=torch.float32, device=f0.device)
         nptr = 0
@@ -97,13 +100,28 @@ class SignalGenerator:
                                                       float(self.noise_amp), _stream(f0.device)))
         return out
 
+    def _sinusoid_host(self, f0, noise=None):
+        """Host tensors (DataLoader workers): the reference's op sequence, features.py:188-195."""
+        B, _, T = f0.size()
+        n = T * self.hop_size
+        vuv = torch.nn.functional.interpolate((f0 > 0) * torch.ones_like(f0), n)
+        radious = (torch.nn.functional.interpolate(f0, n) / self.sample_rate) % 1
+        sine = vuv * torch.sin(torch.cumsum(radious, dim=2) * 2 * np.pi) * self.sine_amp
+        if self.noise_amp > 0:
+            noise_amp = vuv * self.noise_amp + (1.0 - vuv) * self.noise_amp / 3.0
+            if noise is None:
+                noise = torch.randn((B, 1, n), device=f0.device)
+            sine = sine + noise * noise_amp
+        return sine
+
     @torch.no_grad()
     def vuv_binary(self, f0):
         return ((f0 > 0) * torch.ones_like(f0)).repeat_interleave(self.hop_size, dim=2)
 
 
 def pcm16(wave):
-    """Waveform tensor (any shape, CUDA fp32) -> int16 PCM as soundfile's "PCM_16" stores it (saturating)."""
+    """Waveform tensor (any shape, CUDA fp32) -> int16 PCM as soundfile's "PCM_16" stores it: libsndfile's clipping
+    conversion, floor(x * 32768) saturated to int16 (see csrc/excitation.cuh: restated, libsndfile is not in this image)."""
     _require_cuda(wave, "pcm16")
     w = wave.to(torch.float32).contiguous()
     out = torch.empty(w.shape, dtype=torch.int16, device=w.device)

@@ -64,6 +64,17 @@ def _conv_wb(conv):
     return [_f32c(effective_weight(conv)), _f32c(conv.bias)]
 
 
+def _refuse_grad(module, *tensors):
+    """The standalone sub-blocks are inference-only entry points (their outputs carry no ``grad_fn``): refuse a
+    call that expects gradients instead of dropping them silently.  Training goes through ``FastSVCGenerator``."""
+    if torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters())
+                                    or any(t is not None and t.requires_grad for t in tensors)):
+        raise RuntimeError(
+            f"{type(module).__name__}.forward is inference-only in the B200-native build (no autograd through the "
+            "standalone block); call it under torch.no_grad(), or train through FastSVCGenerator.forward, which has "
+            "a native backward.")
+
+
 class FastSVCUpsampleNet(nn.Module):
     """FastSVC upsampling block (reference fastsvc.py:34-140).
 
@@ -93,6 +104,7 @@ class FastSVCUpsampleNet(nn.Module):
         """x (B, C_in, T); s = (scale, shift), l = (scale, shift), each (B, C, T*r); -> (B, C, T*r)."""
         s_scale, s_shift = s
         l_scale, l_shift = l
+        _refuse_grad(self, x, s_scale, s_shift, l_scale, l_shift, spk_emb)
         _require_cuda(x, s_scale, s_shift, l_scale, l_shift, spk_emb)
         lib = abi.load()
         x, s_scale, s_shift, l_scale, l_shift, spk_emb = map(_f32c, (x, s_scale, s_shift, l_scale, l_shift, spk_emb))
@@ -137,6 +149,7 @@ class FastSVCDownsampleNet(nn.Module):
 
     def forward(self, x):
         """x (B, C_in, T) -> (B, C, T / scale); T must be divisible by the scale."""
+        _refuse_grad(self, x)
         _require_cuda(x)
         lib = abi.load()
         x = _f32c(x)
@@ -170,6 +183,7 @@ class FastSVCFiLMNet(nn.Module):
 
     def forward(self, x):
         """x (B, C, T) -> (scale, shift), each (B, C, T)."""
+        _refuse_grad(self, x)
         _require_cuda(x)
         lib = abi.load()
         x = _f32c(x)
@@ -313,7 +327,8 @@ class FastSVCGenerator(nn.Module):
             return generator_forward_with_grad(self, x, s, l, spk_emb)
         return self._forward_cuda(x, s, l, spk_emb)
 
-    def _forward_cuda(self, x, s, l, spk_emb=None):
+    def _check_inputs(self, x, s, l, spk_emb):
+        """Shape validation shared by every entry point; returns (B, frames, T, spk_emb expanded to B rows)."""
         if x.dim() != 3 or s.dim() != 3 or l.dim() != 3:
             raise ValueError("x, s, l must be (B, C, T) tensors")
         B, cin, frames = x.shape
@@ -329,7 +344,11 @@ class FastSVCGenerator(nn.Module):
             if spk_emb.dim() != 2 or spk_emb.shape[1] != self.spk_emb_size or spk_emb.shape[0] not in (1, B):
                 raise ValueError(f"spk_emb must be ({B}, {self.spk_emb_size}), got {tuple(spk_emb.shape)}")
             if spk_emb.shape[0] != B:
-                spk_emb = spk_emb.expand(B, -1)
+                spk_emb = spk_emb.expand(B, -1)   # the (1, S) target speaker of decode_fastsvc.py:156-158
+        return B, frames, T, spk_emb
+
+    def _forward_cuda(self, x, s, l, spk_emb=None):
+        B, frames, T, spk_emb = self._check_inputs(x, s, l, spk_emb)
         device = x.device
         x, s, l, spk_emb = map(_f32c, (x, s, l, spk_emb))
         with torch.cuda.device(device):
@@ -348,17 +367,19 @@ class FastSVCGenerator(nn.Module):
         forward, D2H copy of the waveform, all enqueued on the current stream of
         the module's device by ``fsvc_forward_host``.  Returns the (pinned) host
         output tensor; synchronise the stream before reading it."""
-        device = next(self.parameters()).device
-        if device.type != "cuda":
-            raise RuntimeError("FastSVC (B200-native) needs its parameters on a CUDA device: no CPU fallback")
         for t in (x, s, l, spk_emb):
             if t is not None and t.is_cuda:
                 raise ValueError("forward_host takes host tensors")
-        B, _, frames = x.shape
-        T = frames * self.hop_size
-        x, s, l, spk_emb = map(_f32c, (x, s, l, spk_emb))
+        B, frames, T, spk_emb = self._check_inputs(x, s, l, spk_emb)
+        device = next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("FastSVC (B200-native) needs its parameters on a CUDA device: no CPU fallback")
+        x, s, l, spk_emb = map(_f32c, (x, s, l, spk_emb))   # .contiguous() materialises an expanded (1, S) speaker
         if out is None:
             out = torch.empty((B, self.out_channels, T), dtype=torch.float32).pin_memory()
+        elif tuple(out.shape) != (B, self.out_channels, T) or out.dtype != torch.float32 or out.is_cuda \
+                or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous host fp32 tensor of shape {(B, self.out_channels, T)}")
         with torch.cuda.device(device):
             handle = self._engine(device)
             self._sync_weights(handle, device)
@@ -374,7 +395,7 @@ class FastSVCGenerator(nn.Module):
         """Per-launch device times of one forward (``fsvc_forward_profile``): list of dicts
         {label, ms, flops, bytes}.  Synchronises; for benchmarking only."""
         _require_cuda(x, s, l, spk_emb)
-        B, _, frames = x.shape
+        B, frames, _, spk_emb = self._check_inputs(x, s, l, spk_emb)
         device = x.device
         x, s, l, spk_emb = map(_f32c, (x, s, l, spk_emb))
         with torch.cuda.device(device):

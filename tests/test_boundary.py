@@ -68,6 +68,42 @@ def test_constructor_errors_and_cpu_refusal():
         g.downsampling_loop(torch.zeros(1, 1, 4).cuda() if torch.cuda.is_available() else torch.zeros(1, 1, 4), 7, [])
 
 
+def test_standalone_blocks_refuse_to_drop_gradients():
+    """the block forwards return tensors without grad_fn; a grad-expecting call must raise, not train nothing
+    (tacotron2.py:458-459 builds trainable FastSVCFiLMNet submodules)."""
+    import harana.models as M
+    film = M.FastSVCFiLMNet(8)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        film(torch.zeros(1, 8, 4))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        film(torch.zeros(1, 8, 4))
+    down = M.FastSVCDownsampleNet(1, 8, 2)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        down(torch.zeros(1, 1, 4))
+    up = M.FastSVCUpsampleNet(8, 8, 2, 4)
+    z = torch.zeros(1, 8, 8)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        up(torch.zeros(1, 8, 4), (z, z), (z, z))
+
+
+def test_forward_host_validates_shapes_before_touching_buffers():
+    """fsvc_forward_host copies B*S / B*T floats from the host pointers -- every shape must be checked
+    (and a (1, S) speaker expanded) before the call."""
+    import harana.models as M
+    g = M.FastSVCGenerator(in_channels=8, mid_channels=[8, 8], upsampling_scales=[2, 2], spk_emb_size=4)
+    x, s, l = torch.zeros(2, 8, 3), torch.zeros(2, 1, 12), torch.zeros(2, 1, 12)
+    with pytest.raises(ValueError, match="s and l must be"):
+        g.forward_host(x, torch.zeros(2, 1, 11), l)
+    with pytest.raises(ValueError, match="channels"):
+        g.forward_host(torch.zeros(2, 7, 3), s, l)
+    with pytest.raises(ValueError, match="spk_emb must be"):
+        g.forward_host(x, s, l, torch.zeros(3, 4))
+    B, frames, T, spk = g._check_inputs(x, s, l, torch.ones(1, 4))
+    assert (B, frames, T) == (2, 3, 12) and tuple(spk.shape) == (2, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):       # parameters on the CPU
+        g.forward_host(x, s, l, torch.ones(1, 4))
+
+
 def test_layers_semantics_cpu():
     from harana.layers import Squeeze2d, Stretch2d
     import numpy as np

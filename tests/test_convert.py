@@ -144,7 +144,7 @@ def test_batched_conversion_equals_batch1_decoding(tmp_path):
         f0_o = fo.f0_convert(np.squeeze(u.f0, 1), src_stats[u.utt_id], trg_stats).astype(np.float32)[None, None]
         s_o = fo.sinusoid(f0_o, None, 16000, 160, 0.1, 0.0)
         y_o = onp.generator_forward(params, u.ppg.T[None], s_o, u.lft.T[None], trg_emb)
-        pcm_o = np.clip(np.rint(y_o.reshape(-1) * np.float32(32767.0)), -32768, 32767)
+        pcm_o = fo.pcm16(y_o.reshape(-1)).astype(np.float64)
         clipped = np.abs(y_o.reshape(-1)) >= 0.999
         assert np.abs(got[u.utt_id].astype(np.int64) - pcm_o)[~clipped].max() <= 34
 

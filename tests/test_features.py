@@ -39,11 +39,34 @@ def test_f0_convert_matches_reference_golden():
     assert np.allclose(st, [lf.mean(), lf.std()])
 
 
-def test_signal_generator_has_no_cpu_fallback():
+@pytest.mark.parametrize("name", SINE_CASES)
+def test_signal_generator_host_tensors_match_reference_golden(name):
+    """Host tensors = the data-pipeline use (the reference's Collater runs SignalGenerator on the CPU in DataLoader
+    workers, train_fastsvc.py:546): the reference's torch ops, bit for bit; the seeded draw is the reference's."""
     from harana.utils.features import SignalGenerator
-    gen = SignalGenerator(sample_rate=16000, hop_size=160, signal_types=["sine"])
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
-        gen(torch.zeros(1, 1, 4))
+    g = load_golden(name)
+    B, frames, hop, sr, samp, namp = _meta(g)
+    gen = SignalGenerator(sample_rate=sr, hop_size=hop, sine_amp=samp, noise_amp=namp, signal_types=["sine"])
+    out = gen.sinusoid(torch.from_numpy(g["f0"]), noise=torch.from_numpy(g["noise"]))
+    assert np.array_equal(out.numpy(), g["out"])
+    seed = {"sine_b2_f20": 11, "sine_b3_f100": 12, "sine_b1_f500": 13, "sine_nonoise_b2_f33": 14,
+            "sine_hop64_24k_b2_f50": 15}[name]
+    torch.manual_seed(seed)
+    assert np.array_equal(gen(torch.from_numpy(g["f0"])).numpy(), g["out"])
+    uv = SignalGenerator(sample_rate=sr, hop_size=hop, signal_types=["uv"])(torch.from_numpy(g["f0"]))
+    assert np.array_equal(uv.numpy(), g["uv"])
+
+
+def test_pcm16_oracle_known_answers():
+    """libsndfile f2les_clip_array with clipping on (what soundfile.write(..., "PCM_16") runs): top 16 bits of
+    lrintf(x * 2^31), i.e. floor(x * 32768) saturated."""
+    x = np.array([0, 1, -1, 0.5 / 32768, -0.5 / 32768, 1 / 32768, -1 / 32768, 32767 / 32768, 0.99999, -0.99999, 1.5,
+                  -1.5, 1e-9, -1e-9, 0.25, -0.25], dtype=np.float32)
+    want = [0, 32767, -32768, 0, -1, 1, -1, 32767, 32767, -32768, 32767, -32768, 0, -1, 8192, -8192]
+    assert fo.pcm16(x).tolist() == want
+    rs = np.random.RandomState(1)
+    y = rs.uniform(-1.0, 1.0, 10000).astype(np.float32)
+    assert np.array_equal(fo.pcm16(y), np.floor(y.astype(np.float64) * 32768.0).clip(-32768, 32767).astype(np.int16))
 
 
 @pytest.mark.gpu
@@ -93,7 +116,8 @@ def test_cuda_excitation_draws_noise_like_the_reference():
 def test_pcm16_matches_soundfile_rule():
     from svcc23_fastsvc_b200.features import pcm16
     rs = np.random.RandomState(0)
-    x = np.concatenate([rs.uniform(-1.2, 1.2, 100000), [0.0, 1.0, -1.0, 0.5 / 32767, 1.5 / 32767, 2.5 / 32767]]).astype(np.float32)
+    x = np.concatenate([rs.uniform(-1.2, 1.2, 100000), [0.0, 1.0, -1.0, 0.5 / 32768, -0.5 / 32768, 1.0 / 32768, -1.0 / 32768, 32767.0 / 32768, 0.99999, -0.99999,
+                             1e-9, -1e-9]]).astype(np.float32)
     y = pcm16(torch.from_numpy(x).cuda()).cpu().numpy()
-    want = np.clip(np.rint(x.astype(np.float32) * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    want = fo.pcm16(x)
     assert y.dtype == np.int16 and np.array_equal(y, want)
