@@ -92,8 +92,10 @@ def test_blocks_match_reference_golden(precision):
                      (yu, "up_out"), (yn, "up_out_nospk")):
         err = np.abs(got.cpu().numpy() - gold[key]).max()
         assert err <= (1e-4 if precision == "fp32" else 1e-3), (key, err)
-    with pytest.raises(ValueError):
+    with torch.no_grad(), pytest.raises(ValueError):
         d1(torch.zeros(1, 24, 23, device=_cuda()))  # T not divisible by the scale
+    with pytest.raises(RuntimeError, match="inference-only"):   # grad-enabled call on a block: refused, not dropped
+        f0(y0)
 
 
 @pytest.mark.parametrize("precision", MODES)
