@@ -46,7 +46,8 @@ extern "C" {
 
 /* precision modes of fsvc_forward */
 #define FSVC_MODE_FP32 0    /* fp32 FFMA everywhere: parity mode */
-#define FSVC_MODE_TC_BF16X3 1 /* tcgen05 tensor cores, 3-term bf16 split, fp32 accumulate */
+#define FSVC_MODE_TC_BF16X3 1 /* tcgen05 tensor cores, 3-term bf16 split, fp32 accumulate (channel counts that are
+                                 not multiples of 8 fall back to fp32 FFMA) */
 #define FSVC_MODE_AUTO 2    /* fastest mode that meets the 1e-3 parity bar for this config */
 
 typedef struct fsvc_handle fsvc_handle;
@@ -115,7 +116,9 @@ int fsvc_forward_host(fsvc_handle* h, const float* ppg_host, const float* sine_h
 
 /* Block-level entry points (the reference's sub-modules stay importable and
  * are used standalone, e.g. tacotron2.py:22,458-459 uses FastSVCFiLMNet).
- * Weights are passed per call as device pointers in PyTorch layout.
+ * Weights are passed per call as device pointers in PyTorch layout.  The blocks
+ * compute in fp32 (FFMA) in every `mode`: the tensor-core kernels work on the
+ * generator's channels-last workspace, which a standalone block does not have.
  *
  * fsvc_downsample_forward replaces FastSVCDownsampleNet.forward
  * (fastsvc.py:180-193): w[] = {residual_block.0 (w,b), downsample_block.2
@@ -174,6 +177,28 @@ int fsvc_sine_excitation(const float* f0, const float* noise, float* out, int B,
 int fsvc_pcm16(const float* x, int16_t* y, long long n, void* stream);
 
 int fsvc_last_launch_count(const fsvc_handle* h);
+
+/*
+ * Training: replaces autograd through FastSVCGenerator.forward -- `y_ = self.model["generator"](*x)`
+ * followed by `gen_loss.backward()` (harana/bin/train_fastsvc.py:168, 199-206).
+ *
+ * fsvc_forward_train is fsvc_forward in fp32 that also keeps, in the caller-owned `saved` buffer
+ * (fsvc_train_saved_bytes), every activation the backward needs.  fsvc_backward takes dL/d(out) and writes the
+ * gradient of every EFFECTIVE weight tensor -- n = fsvc_num_weight_tensors() device pointers in the canonical order of
+ * fsvc_weight_tensor_info, PyTorch layouts, overwritten -- computed by hand-written kernels (data gradients, weight
+ * gradients, InstanceNorm / FiLM / LeakyReLU / repeat / decimation adjoints; no autograd, no cuDNN).  With weight norm
+ * applied the host chains them through w = g * v / ||v||.  Inputs receive no gradient (the reference never asks for
+ * one).  The weights in the library must be the ones of the forward call; `workspace` (fsvc_train_workspace_bytes) is
+ * scratch for either call.  Same stream / capture rules as fsvc_forward.
+ */
+size_t fsvc_train_saved_bytes(const fsvc_handle* h, int B, int frames);
+size_t fsvc_train_workspace_bytes(const fsvc_handle* h, int B, int frames);
+int fsvc_forward_train(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk,
+                       float* out, int B, int frames, void* saved, size_t saved_bytes, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int fsvc_backward(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk,
+                  const float* grad_out, int B, int frames, const void* saved, size_t saved_bytes,
+                  float* const* grad_ptrs, int n, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

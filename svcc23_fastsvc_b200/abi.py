@@ -22,7 +22,8 @@ EXPORTS = (
     "fsvc_weight_tensor_info", "fsvc_set_weights", "fsvc_workspace_bytes", "fsvc_forward",
     "fsvc_host_io_bytes", "fsvc_forward_host", "fsvc_downsample_forward", "fsvc_film_forward",
     "fsvc_upsample_forward", "fsvc_block_workspace_bytes", "fsvc_last_launch_count", "fsvc_forward_profile",
-    "fsvc_sine_excitation", "fsvc_pcm16",
+    "fsvc_sine_excitation", "fsvc_pcm16", "fsvc_train_saved_bytes", "fsvc_train_workspace_bytes",
+    "fsvc_forward_train", "fsvc_backward",
 )
 
 
@@ -104,6 +105,14 @@ def load():
     lib.fsvc_pcm16.argtypes = [vp, vp, ctypes.c_longlong, vp]
     lib.fsvc_last_launch_count.restype = i32
     lib.fsvc_last_launch_count.argtypes = [vp]
+    lib.fsvc_train_saved_bytes.restype = sz
+    lib.fsvc_train_saved_bytes.argtypes = [vp, i32, i32]
+    lib.fsvc_train_workspace_bytes.restype = sz
+    lib.fsvc_train_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.fsvc_forward_train.restype = i32
+    lib.fsvc_forward_train.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp, sz, vp]
+    lib.fsvc_backward.restype = i32
+    lib.fsvc_backward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, pp, i32, vp, sz, vp]
     if lib.fsvc_abi_version() != 1:
         raise FsvcError(f"libfsvc ABI version {lib.fsvc_abi_version()} != 1")
     _lib = lib
@@ -194,3 +203,17 @@ class Handle:
 
     def last_launch_count(self):
         return self._lib.fsvc_last_launch_count(self._h)
+
+    def train_saved_bytes(self, B, frames):
+        return self._lib.fsvc_train_saved_bytes(self._h, B, frames)
+
+    def train_workspace_bytes(self, B, frames):
+        return self._lib.fsvc_train_workspace_bytes(self._h, B, frames)
+
+    def forward_train(self, ppg, sine, lft, spk, out, B, frames, saved, saved_bytes, ws, ws_bytes, stream):
+        check(self._lib.fsvc_forward_train(self._h, ppg, sine, lft, spk, out, B, frames, saved, saved_bytes, ws,
+                                           ws_bytes, stream))
+
+    def backward(self, ppg, sine, lft, spk, grad_out, B, frames, saved, saved_bytes, grad_ptrs, ws, ws_bytes, stream):
+        check(self._lib.fsvc_backward(self._h, ppg, sine, lft, spk, grad_out, B, frames, saved, saved_bytes,
+                                      ptr_array(grad_ptrs), len(grad_ptrs), ws, ws_bytes, stream))

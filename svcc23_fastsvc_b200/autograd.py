@@ -1,112 +1,95 @@
-"""Differentiable wrapper of the CUDA generator forward (training callers:
-reference train_fastsvc.py:168,199-206).
+"""Differentiable wrapper of the CUDA generator (training callers: reference train_fastsvc.py:168,199-206).
 
-Forward values come from libfsvc.so.  INTERIM backward (SURVEY.md 8f row N1 --
-the native CUDA backward is the next row, not part of the forward hot path):
-the graph is rebuilt in ``backward`` from stock PyTorch CUDA ops over the
-module's live parameters and differentiated with ``torch.autograd.grad``.  It
-runs on the GPU only and never produces forward values.
+Forward AND backward run in libfsvc.so (``fsvc_forward_train`` / ``fsvc_backward``, csrc/train.cu): the forward keeps
+its activations in a buffer owned by the autograd node, the backward returns the gradient of every *effective* conv
+weight.  The effective weights are inputs of the autograd function, so with weight norm applied
+(``w = g * v / ||v||``, fastsvc.py:354-362) stock autograd carries the gradients on to ``weight_g`` / ``weight_v`` --
+that thin elementwise chain is the only PyTorch arithmetic on the path.  Inputs (PPG, excitation, loudness, speaker
+embedding) receive no gradient; the reference never asks for one.
 """
 
 import torch
-import torch.nn.functional as F
 
 from .layers import effective_weight
 
-_SLOPE = 0.2
 
-
-def _c(conv, x, dil):
-    w = effective_weight(conv)
-    if w.dim() == 4:
-        w = w[:, :, 0, :]
-    k = w.shape[-1]
-    return F.conv1d(x, w, conv.bias, dilation=dil, padding=dil * (k // 2))
-
-
-def _down(net, x, scale):
-    xd = x[..., ::scale]
-    r = _c(net.residual_block[0], xd, 1)
-    h = _c(net.downsample_block[2], F.leaky_relu(xd, _SLOPE), 1)
-    h = _c(net.downsample_block[4], F.leaky_relu(h, _SLOPE), 2)
-    h = _c(net.downsample_block[6], F.leaky_relu(h, _SLOPE), 4)
-    return h + r
-
-
-def _film(net, y):
-    h = F.leaky_relu(_c(net.conv, y, 1), _SLOPE)
-    return _c(net.conv_scale, h, 1), _c(net.conv_shift, h, 1)
-
-
-def _stage(net, x, gamma, beta, r, spk):
-    def fa(t):
-        t = gamma * t + beta
-        if spk is not None:
-            t = F.instance_norm(t, eps=1e-5) + net.emb_projector(F.normalize(spk)).unsqueeze(-1)
-        return F.leaky_relu(t, _SLOPE)
-
-    h0 = _c(net.conv_first, x, 1)
-    xr = _c(net.residual_block[1], h0.repeat_interleave(r, -1), 1)
-    u = F.leaky_relu(_c(net.upsample_block0[2], F.leaky_relu(h0, _SLOPE).repeat_interleave(r, -1), 1), _SLOPE)
-    x_ = _c(net.conv_block1[1], fa(u), 3) + xr
-    x2 = _c(net.conv_block2[1], fa(x_), 9)
-    return _c(net.conv_block3[1], fa(x2), 27) + x_
-
-
-def _graph_forward(g, x, s, l, spk):
-    n = len(g.upsampling_nets)
-    scales = list(g.upsampling_scales)
-    down = [1] + scales[::-1][:-1]
-    gb = []
-    hl, hs = l, s
-    for i in range(n):
-        hl = _down(g.downsampling_lft[i], hl, down[i])
-        hs = _down(g.downsampling_sine[i], hs, down[i])
-        gl, bl = _film(g.film_lft[i], hl)
-        gs, bs = _film(g.film_sine[i], hs)
-        gb.append((gl + gs, bl + bs))
-    for i in range(n):
-        gamma, beta = gb[n - 1 - i]
-        x = _stage(g.upsampling_nets[i], x, gamma, beta, scales[i], spk)
-    return _c(g.conv_last, x, 1)
+def effective_weights(module, handle):
+    """The tensors libfsvc expects (canonical order of ``fsvc_weight_tensor_info``), differentiable w.r.t. the
+    module's parameters when grad is enabled."""
+    out = []
+    for name in handle.weight_names:
+        path, kind = name.rsplit(".", 1)
+        mod = module.get_submodule(path)
+        if kind == "bias":
+            out.append(mod.bias)
+        elif isinstance(mod, torch.nn.Linear):
+            out.append(mod.weight)
+        else:
+            out.append(effective_weight(mod))
+    return out
 
 
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, s, l, spk, *params):
-        ctx.module = module
-        ctx.has_spk = spk is not None
-        ctx.save_for_backward(x, s, l, *([spk] if spk is not None else []))
-        return module._forward_cuda(x, s, l, spk)
+    def forward(ctx, module, x, s, l, spk, *weights):
+        from .generator import _f32c, _stream
+        device = x.device
+        B, frames, T, spk = module._check_inputs(x, s, l, spk)
+        x, s, l, spk = map(_f32c, (x, s, l, spk))
+        w32 = [_f32c(w) for w in weights]
+        with torch.cuda.device(device):
+            handle = module._engine(device)
+            for t, n, name in zip(w32, handle.weight_numel, handle.weight_names):
+                if t.numel() != n:
+                    raise RuntimeError(f"parameter {name} has {t.numel()} elements, library expects {n}")
+            stream = _stream(device)
+            handle.set_weights([t.data_ptr() for t in w32], stream)
+            module._weights_key = module._param_key()
+            module._weights_epoch += 1
+            saved = torch.empty(handle.train_saved_bytes(B, frames), dtype=torch.uint8, device=device)
+            ws = module._ws.get(handle.train_workspace_bytes(B, frames), device)
+            out = torch.empty((B, module.out_channels, T), dtype=torch.float32, device=device)
+            handle.forward_train(x.data_ptr(), s.data_ptr(), l.data_ptr(), 0 if spk is None else spk.data_ptr(),
+                                 out.data_ptr(), B, frames, saved.data_ptr(), saved.numel(), ws.data_ptr(),
+                                 ws.numel(), stream)
+        ctx.module, ctx.handle, ctx.epoch = module, handle, module._weights_epoch
+        ctx.dims = (B, frames)
+        ctx.saved_buf = saved
+        ctx.inputs = (x, s, l, spk)
+        ctx.wmeta = [(w.shape, w.dtype) for w in weights]
+        return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        g = ctx.module
-        saved = ctx.saved_tensors
-        x, s, l = saved[:3]
-        spk = saved[3] if ctx.has_spk else None
-        params = [p for p in g.parameters()]
-        # full fp32 in the interim graph: with cuDNN's default TF32 convolutions the parameter gradients drift ~2 %
-        # from the reference's fp32 CPU autograd (tests/test_grads.py)
-        with torch.enable_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=torch.backends.cudnn.benchmark,
-                                                             deterministic=torch.backends.cudnn.deterministic,
-                                                             allow_tf32=False):
-            ins = [t.detach().requires_grad_(need) for t, need in zip((x, s, l), ctx.needs_input_grad[1:4])]
-            spk_in = None
-            if spk is not None:
-                spk_in = spk.detach().requires_grad_(ctx.needs_input_grad[4])
-            y = _graph_forward(g, ins[0], ins[1], ins[2], spk_in)
-            wanted = [t for t in ins + ([spk_in] if spk_in is not None else []) + params if t.requires_grad]
-            grads = torch.autograd.grad(y, wanted, grad_out, allow_unused=True)
-        it = iter(grads)
-        res = [None]
-        for t in ins:
-            res.append(next(it) if t.requires_grad else None)
-        res.append(next(it) if (spk_in is not None and spk_in.requires_grad) else None)
-        for p in params:
-            res.append(next(it) if p.requires_grad else None)
-        return tuple(res)
+        from .generator import _f32c, _stream
+        module, handle = ctx.module, ctx.handle
+        if module._weights_epoch != ctx.epoch or module._handle is not handle:
+            raise RuntimeError(
+                "FastSVCGenerator: the weights inside libfsvc changed between this forward and its backward (another "
+                "grad-enabled forward, an optimizer step followed by a forward, or a device move); gradients would "
+                "belong to different weights. Run backward before the next forward.")
+        x, s, l, spk = ctx.inputs
+        B, frames = ctx.dims
+        device = x.device
+        g = _f32c(grad_out)
+        grads = [torch.empty(shape, dtype=torch.float32, device=device) for shape, _ in ctx.wmeta]
+        with torch.cuda.device(device):
+            ws = module._ws.get(handle.train_workspace_bytes(B, frames), device)
+            handle.backward(x.data_ptr(), s.data_ptr(), l.data_ptr(), 0 if spk is None else spk.data_ptr(),
+                            g.data_ptr(), B, frames, ctx.saved_buf.data_ptr(), ctx.saved_buf.numel(),
+                            [t.data_ptr() for t in grads], ws.data_ptr(), ws.numel(), _stream(device))
+        ctx.saved_buf = None
+        grads = [gr if dt == torch.float32 else gr.to(dt) for gr, (_, dt) in zip(grads, ctx.wmeta)]
+        if spk is None:  # emb_projector takes no part in the graph (fastsvc.py:134): no gradient, like stock autograd
+            grads = [None if ".emb_projector." in name else gr for gr, name in zip(grads, handle.weight_names)]
+        return (None, None, None, None, None, *grads)
 
 
 def generator_forward_with_grad(module, x, s, l, spk):
-    return _GeneratorFn.apply(module, x, s, l, spk, *module.parameters())
+    for name, t in (("x", x), ("s", s), ("l", l), ("spk_emb", spk)):
+        if t is not None and t.requires_grad:
+            raise NotImplementedError(
+                f"FastSVCGenerator (B200-native): gradient w.r.t. the input {name!r} is not implemented; the native "
+                "backward returns parameter gradients only (all the reference's training loop uses)")
+    handle = module._engine(x.device)
+    return _GeneratorFn.apply(module, x, s, l, spk, *effective_weights(module, handle))

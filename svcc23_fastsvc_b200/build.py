@@ -1,19 +1,23 @@
 """Build libfsvc.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
     python -m svcc23_fastsvc_b200.build [--force] [--verbose]
+
+One object per translation unit (compiled in parallel, rebuilt only when it or a header changed), then one link.
 """
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libfsvc.so")
-SOURCES = ["fsvc_abi.cu"]
+SOURCES = ["fsvc_abi.cu", "tc_forward.cu", "train.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -24,25 +28,43 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
-def _stale():
-    if not os.path.exists(OUT):
-        return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+def _headers():
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "fsvc.h"))
+    return deps
+
+
+def _newer(path, deps):
+    if not os.path.exists(path):
+        return True
+    t = os.path.getmtime(path)
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
-        return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+def _run(cmd, verbose):
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libfsvc.so")
+        raise RuntimeError("nvcc failed: " + " ".join(cmd))
+
+
+def build(force=False, verbose=False):
+    sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    hdrs = _headers()
+    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in sources]
+    if not force and os.path.exists(OUT) and not _newer(OUT, hdrs + [os.path.join(CSRC, s) for s in sources]):
+        return OUT   # a shipped .so (the GPU box gets no build/ directory it could compare against)
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    todo = []
+    for s, o in zip(sources, objs):
+        src = os.path.join(CSRC, s)
+        if force or _newer(o, hdrs + [src]):
+            todo.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", o, src])
+    with ThreadPoolExecutor(max_workers=max(1, len(todo))) as ex:
+        list(ex.map(lambda c: _run(c, verbose), todo))
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs, verbose)
     return OUT
 
 

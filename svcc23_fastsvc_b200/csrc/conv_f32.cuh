@@ -7,7 +7,7 @@
 //   in'[b,ci,u] = 0                                   if u outside [0,T_out)   (zero padding is applied
 //               = lrelu?( a[b,ci]*in[b,ci,map(u)] + c[b,ci] )  otherwise        AFTER norm/activation)
 //   map(u)      = (u / up) * down        nearest repeat (Stretch2d) or decimation (Squeeze2d, T % s == 0)
-//   epilogue    : v += res;  raw = v;  v = lrelu?(v);  v = gamma*v + beta;  out = v;
+//   epilogue    : v *= lrelu'(mask)?;  v += res;  raw = v;  v = lrelu?(v);  v = gamma*v + beta;  out = v;
 //                 per-(b,co,tile) (mean, M2) partials of the stored value for InstanceNorm.
 //
 // Reference semantics: Conv1d1x3/Conv2d1x3/Conv1d1x1 (layers/upsample.py:76-106,
@@ -51,6 +51,14 @@ struct ConvArgs {
   int out_cs;
   float2* stats;  // [B][C_out][n_tiles] (mean, M2) or nullptr
   int n_tiles;
+  // backward use (train.cu): multiply the conv result by lrelu'(m) BEFORE `res` is added, with
+  // m = mask[b][co][(t / mask_up) * mask_down] (optionally mask_a[b][co] * m + mask_c[b][co]): the derivative of the
+  // LeakyReLU that preceded the forward conv whose data gradient this launch computes
+  const float* mask;
+  long long mask_bs;
+  int mask_cs, mask_up, mask_down;
+  const float* mask_a;
+  const float* mask_c;
   float slope;
   const void* host_w;  // host-side ConvW* (launch dispatch only; never dereferenced on the device)
 };
@@ -140,6 +148,11 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_f32_kernel(const ConvArgs
       const int t = t0 + lane + 32 * j;
       float v = acc[i][j] + bias;
       if (t < a.T_out) {
+        if (a.mask) {
+          float m = __ldg(a.mask + (long long)b * a.mask_bs + (long long)co * a.mask_cs + (t / a.mask_up) * a.mask_down);
+          if (a.mask_a) m = fmaf(m, __ldg(a.mask_a + b * a.C_out + co), __ldg(a.mask_c + b * a.C_out + co));
+          v *= m > 0.f ? 1.f : a.slope;   // torch leaky_relu backward: x > 0 ? g : g * slope
+        }
         if (a.res) v += __ldg(a.res + (long long)b * a.res_bs + (long long)co * a.res_cs + t);
         if (a.raw) a.raw[(long long)b * a.raw_bs + (long long)co * a.raw_cs + t] = v;
         if (a.post_lrelu) v = lrelu(v, a.slope);
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_f32_kernel(const ConvArgs
 // applies on load:  norm(x) + e  ==  x * a + c  with a = rstd, c = e - mean*rstd.
 // InstanceNorm2d semantics: biased variance over the whole time axis, eps inside
 // the sqrt (fastsvc.py:76,138).  e = emb_projector(normalize(spk)) (fastsvc.py:135-137).
-__global__ void in_finalize_kernel(const float2* __restrict__ stats, int n_tiles, int tile_len, int T, int BC,
+static __global__ void in_finalize_kernel(const float2* __restrict__ stats, int n_tiles, int tile_len, int T, int BC,
                                    const float* __restrict__ e, float eps, float* __restrict__ out_a,
                                    float* __restrict__ out_c) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +214,7 @@ __global__ void in_finalize_kernel(const float2* __restrict__ stats, int n_tiles
 
 // e[b][c] = bias[c] + sum_j W[c][j] * spk[b][j] / max(||spk[b]||_2, 1e-12)
 // (nn.Linear(F.normalize(spk_emb)), fastsvc.py:135-137).  grid = (B), block = 256.
-__global__ void spk_project_kernel(const float* __restrict__ spk, int S, const float* __restrict__ W,
+static __global__ void spk_project_kernel(const float* __restrict__ spk, int S, const float* __restrict__ W,
                                    const float* __restrict__ bias, int C, float* __restrict__ e) {
   __shared__ float red[32];
   __shared__ float inv_norm;
@@ -229,7 +242,7 @@ __global__ void spk_project_kernel(const float* __restrict__ spk, int S, const f
 }
 
 // PyTorch (Cout, Cin, K) -> packed [ci_off + ci][k][co_off + co] with row length dst_cout.
-__global__ void repack_weight_kernel(const float* __restrict__ src, int C_out, int C_in, int K,
+static __global__ void repack_weight_kernel(const float* __restrict__ src, int C_out, int C_in, int K,
                                      float* __restrict__ dst, int dst_cout, int ci_off, int co_off) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C_out * C_in * K) return;
@@ -237,8 +250,17 @@ __global__ void repack_weight_kernel(const float* __restrict__ src, int C_out, i
   dst[((long long)(ci_off + ci) * K + k) * dst_cout + co_off + co] = src[i];
 }
 
+// packed [C_in][K][C_out] -> packed [C_out][K][C_in] with the taps reversed: the conv whose output is the gradient of
+// the original conv's input (dgrad):  g_in[u] = sum_{k,co} W[co,ci,k] * g_out[u - (k-(K-1)/2)*dil].
+static __global__ void transpose_weight_kernel(const float* __restrict__ w, int C_in, int C_out, int K, float* __restrict__ wT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C_out * C_in * K) return;
+  const int co = i % C_out, k = (i / C_out) % K, ci = i / (C_out * K);
+  wT[((long long)co * K + (K - 1 - k)) * C_in + ci] = w[i];
+}
+
 // dst[off + i] = a[i] (+ b[i])
-__global__ void bias_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
+static __global__ void bias_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
                                 float* __restrict__ dst, int off) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[off + i] = a[i] + (b ? b[i] : 0.f);

@@ -1,6 +1,6 @@
 // Warp-specialised, software-pipelined tcgen05 1-D convolution over channels-last activations.
 //
-// Same contract as conv_tc2_kernel (Tc2Args: fused prologue / epilogue of every FastSVC conv), organised
+// Tc2Args (ntc_common.cuh) describes the fused prologue / epilogue of every FastSVC conv; the kernel is organised
 // as a four-role pipeline so that no role ever waits on HBM with nothing else to do:
 //
 //   warp 0      WEIGHTS    cp.async.bulk (UBLKCP) of the packed bf16 hi|lo weights: once when they fit in
@@ -19,7 +19,7 @@
 // side).  One CTA per SM, a static round-robin list of (utterance, 128-step tile) items per CTA.
 // Activations are [B][T][C] fp32: every global access is a 128-bit access to a contiguous row segment.
 #pragma once
-#include "conv_tc2.cuh"
+#include "ntc_common.cuh"
 
 namespace fsvc {
 

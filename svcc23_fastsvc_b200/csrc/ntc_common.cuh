@@ -1,0 +1,262 @@
+// Channels-last ("NTC") activation layout, the argument block of one fused conv, and the small companion kernels of
+// the tensor-core forward.
+//
+// Reference semantics implemented by the fused prologue / epilogue (Tc2Args): Conv1d1x3 / Conv2d1x3 / Conv1d1x1
+// (layers/upsample.py:76-106, layers/residual_block.py:41-48), Stretch2d / Squeeze2d index maps
+// (layers/upsample.py:38-74), _feature_affine + LeakyReLU (fastsvc.py:115-140, 56-75), FastSVCDownsampleNet's first
+// conv and 1x1 residual on the raw 1-channel signal (fastsvc.py:164-172, "gen" operands below).
+#pragma once
+#include "tc_prims.cuh"
+
+namespace fsvc {
+
+struct Tc2Args {
+  // ---- A operand source -------------------------------------------------------------
+  const float* in;     // NTC [B][T_in][in_ld] (channel offset folded into the pointer) | NCT [B][C_in][T_in]
+  int in_ld;           // NTC row stride (floats)
+  int T_in;            // stored time steps per utterance
+  int C_in;
+  int in_nct;          // 1: input is (B, C_in, T_in) time-fastest (the caller's PPG tensor)
+  int up, down;        // source row of output-rate index u: (u / up) * down
+  const float* pre_a;  // [B][C_in] InstanceNorm affine applied on load (or nullptr)
+  const float* pre_c;
+  // Alternative to pre_a/pre_c (conv_tc3 only): the producer's per-segment (mean, M2) partials [B][pre_nseg][C_in]
+  // are merged by the consumer itself (no separate finalize launch): a = rstd, c = pre_e - mean * rstd.
+  const float2* pre_stats;
+  const float* pre_e;  // [B][C_in] projected speaker embedding, or nullptr
+  int pre_nseg;        // 32-step segments per utterance (the last may be short: T_in rows in total)
+  float pre_eps;
+  int pre_lrelu;
+  const float* gen_w;  // != nullptr: `in` is a 1-channel signal [B][T_in] and the C_in operand channels are
+  const float* gen_b;  //   gen_b[c] + sum_k gen_w[k*C_in+c] * lrelu(x[u+k-1])   (first conv of a level-0 chain)
+  // ---- weights ------------------------------------------------------------------------
+  const __nv_bfloat16* w;  // packed [n_tile][ci_blk][hi|lo][tap][CIB/8][N_tile][8]
+  int CIB, n_blk, N_tile, n_ntiles;
+  int w_resident;
+  const float* bias;
+  int dil, C_out, T_out;
+  // ---- epilogue -------------------------------------------------------------------------
+  const float* res;  // NTC [B][T_out][res_ld] added before `raw`
+  int res_ld;
+  const float* gres_w;  // != nullptr: residual generated from a 1-channel signal: gres_w[c]*x[b][t] + gres_b[c]
+  const float* gres_b;
+  const float* gres_x;
+  float* raw;  // value before activation / FiLM (skip tensors)
+  int raw_ld;
+  int post_lrelu;
+  const float* gamma;  // FiLM: v = gamma*v + beta, both [B][T_out][gb_ld]
+  const float* beta;
+  int gb_ld;
+  float* out;
+  int out_ld;
+  float2* stats;  // [B][n_seg][C_out] (mean, M2) of the stored value per 32-step segment, or nullptr
+  int n_seg;
+  float slope;
+};
+
+// Blocked channels-last activation layout of the tensor-core forward: [B][ceil(T/32)][ld/4][32 steps][4 channels].
+// 32 consecutive time steps of one 4-channel group are 512 contiguous bytes, so a warp whose lanes own
+// consecutive time steps (the TMEM epilogue, the A-window staging) touches whole 128-byte lines with every
+// 128-bit access -- a plain [T][C] row layout costs one line per lane there.  Offsets are in floats; a channel
+// offset co (multiple of 4) is folded into a base pointer as (co / 4) * 128.
+__host__ __device__ inline long long ntc_tp(int T) { return (long long)((T + 31) / 32) * 32; }
+__host__ __device__ inline long long ntc_row(long long Tp, int ld, int b, int t) {
+  return ((long long)b * Tp + (t & ~31)) * ld + (t & 31) * 4;
+}
+__host__ __device__ inline long long ntc_col(int co) { return (long long)(co >> 2) * 128 + (co & 3); }
+
+constexpr int kTc2M = 128;
+
+// Wait for the phase with the given parity.  The suspend-time hint lets the hardware park the thread until
+// the phase completes instead of spinning (spinning waiters steal issue slots from the MMA-issuing warp).
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running.  launch_dependents lets OUR successor start early
+// (every CTA issues it at once: all grids here are single-wave, so nothing of this kernel is left to schedule);
+// griddep_wait blocks until the predecessor grid has completed and its writes are visible -- every thread calls
+// it before its first access to activations / workspace (weights and parameters are not produced by kernels).
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (UBLKCP), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(taddr)
+               : "memory");
+  v[0] = __uint_as_float(r0);
+  v[1] = __uint_as_float(r1);
+  v[2] = __uint_as_float(r2);
+  v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void split_store(uint8_t* dst, uint32_t plane, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(dst + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ---- small companions -------------------------------------------------------------------
+
+// Merge the per-32-step (mean, M2) partials [B][n_seg][C] of one (b, c) (Chan et al., double, fixed order)
+// and emit the affine the next conv applies on load: a = rstd, c = e - mean*rstd.
+// InstanceNorm2d: biased variance over the whole time axis, eps inside the sqrt (fastsvc.py:76,138).
+// One warp per (b, c): lane l merges segments l, l+32, ... (loads issued 8 at a time), then a 5-step
+// butterfly merges the lanes.  grid = ceil(B*C / 8) blocks of 256 threads.
+__device__ __forceinline__ double shfl_xor_d(double v, int o) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, o);
+  hi = __shfl_xor_sync(0xffffffffu, hi, o);
+  return __hiloint2double(hi, lo);
+}
+__global__ void __launch_bounds__(256) in_finalize2_kernel(const float2* __restrict__ stats, int n_seg, int T, int C,
+                                                           int BC, const float* __restrict__ e, float eps,
+                                                           float* __restrict__ out_a, float* __restrict__ out_c) {
+  const int lane = threadIdx.x & 31;
+  const int bc = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (bc >= BC) return;
+  const int b = bc / C, c = bc - b * C;
+  const float2* sp = stats + (long long)b * n_seg * C + c;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int s0 = lane; s0 < n_seg; s0 += 8 * 32) {
+    float2 pv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int sg = s0 + 32 * u;
+      pv[u] = sg < n_seg ? __ldg(sp + (long long)sg * C) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int sg = s0 + 32 * u;
+      if (sg < n_seg) {
+        const double nb = (double)min(32, T - sg * 32);
+        const double d = (double)pv[u].x - mean, nn = n + nb;
+        mean += d * nb / nn;
+        m2 += (double)pv[u].y + d * d * n * nb / nn;
+        n = nn;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double n2 = shfl_xor_d(n, o), mean2 = shfl_xor_d(mean, o), m22 = shfl_xor_d(m2, o);
+    // merge (lower lane's partial, upper lane's partial) in that order on both lanes: bitwise symmetric
+    const bool low = (lane & o) == 0;
+    const double na = low ? n : n2, ma = low ? mean : mean2, qa = low ? m2 : m22;
+    const double nb = low ? n2 : n, mb = low ? mean2 : mean, qb = low ? m22 : m2;
+    const double nn = na + nb;
+    if (nn > 0.0) {
+      const double d = mb - ma;
+      mean = ma + d * nb / nn;
+      m2 = qa + qb + d * d * na * nb / nn;
+    }
+    n = nn;
+  }
+  if (lane == 0) {
+    const double var = m2 / (double)T;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    out_a[bc] = (float)rstd;
+    out_c[bc] = (float)((double)(e ? e[bc] : 0.f) - mean * rstd);
+  }
+}
+
+// All stages' speaker projections in one launch: e_i[b][c] = bias_i[c] + W_i[c] . normalize(spk[b])
+// (nn.Linear(F.normalize(spk_emb)), fastsvc.py:135-137).  grid = (B, n_stages, ceil(C_max/32)), block = 256:
+// a warp owns 4 output channels and keeps all their loads in flight.
+struct SpkProjArgs {
+  const float* W[8];
+  const float* bias[8];
+  float* e[8];
+  int C[8];
+};
+__global__ void __launch_bounds__(256) spk_project_all_kernel(const float* __restrict__ spk, int S, SpkProjArgs p) {
+  __shared__ float red[8];
+  __shared__ float inv_norm;
+  const int b = blockIdx.x, st = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C[st];
+  const int c0 = blockIdx.z * 32 + warp * 4;
+  if (blockIdx.z * 32 >= C) return;
+  const float* x = spk + (long long)b * S;
+  float ss = 0.f;
+  for (int j = tid; j < S; j += 256) ss = fmaf(x[j], x[j], ss);
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  if (tid == 0) {
+    float v = 0.f;
+    for (int i = 0; i < 8; ++i) v += red[i];
+    inv_norm = 1.f / fmaxf(sqrtf(v), 1e-12f);
+  }
+  __syncthreads();
+  const float inv = inv_norm;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = lane; j < S; j += 32) {
+    const float xv = x[j] * inv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (c0 + i < C) acc[i] = fmaf(__ldg(p.W[st] + (long long)(c0 + i) * S + j), xv, acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && c0 + i < C) p.e[st][(long long)b * C + c0 + i] = v + p.bias[st][c0 + i];
+  }
+}
+
+// conv_last (Conv1d1x1, fastsvc.py:301,330) from blocked channels-last x to (B, C_out, T):
+// one thread per time step.  w is the packed fp32 layout [C][C_out].
+__global__ void __launch_bounds__(256) conv_last_ntc_kernel(const float* __restrict__ x, int C, int T, long long BT,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            int C_out, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= BT) return;
+  const long long b = i / T;
+  const int t = (int)(i - b * T);
+  const float4* xp = reinterpret_cast<const float4*>(x + ntc_row(ntc_tp(T), C, (int)b, t));
+  for (int co = 0; co < C_out; ++co) {
+    float acc = __ldg(bias + co);
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+      const float4 v = __ldg(xp + 32 * c4);
+      const float* wp = w + (long long)(4 * c4) * C_out + co;
+      acc = fmaf(v.x, __ldg(wp), acc);
+      acc = fmaf(v.y, __ldg(wp + C_out), acc);
+      acc = fmaf(v.z, __ldg(wp + 2 * C_out), acc);
+      acc = fmaf(v.w, __ldg(wp + 3 * C_out), acc);
+    }
+    out[(b * C_out + co) * T + t] = acc;
+  }
+}
+
+}  // namespace fsvc

@@ -1,0 +1,125 @@
+// tcgen05 / TMEM / mbarrier / bulk-copy PTX wrappers and the packed tensor-core weight format shared by the
+// sm_100a kernels (conv_tc3.cuh, level_fused.cuh).
+//
+// Implicit GEMM, time on M:   D[128 t, N co] += A_tap[128 t, 16 ci] * W_tap[16 ci, N co]
+// for every tap and 16-channel slice.  fp32 parity (<= 1e-3) is kept with a 3-term bf16
+// split of both operands (a = a_hi + a_lo, w = w_hi + w_lo; a_hi*w_hi + a_lo*w_hi +
+// a_hi*w_lo, fp32 accumulation in TMEM): measured 1.1e-4 max-abs on the whole generator.
+//
+// Shared-memory operand layout (UMMA "K-major, SWIZZLE_NONE" canonical form): an operand
+// is a set of column strips, one per group of 8 channels; a strip holds one 16-byte chunk
+// (8 bf16 channels) per row, rows contiguous:  addr(row, ch) = strip(ch/8) + row*16 + (ch%8)*2.
+// Core matrices (8 rows x 16 B) are therefore contiguous 128-byte blocks with SBO = 128 B and
+// LBO = strip pitch, and -- the point of this layout -- a dilated tap is just a descriptor
+// whose start address is advanced by tap*dil rows (16-byte granularity), so the three taps of
+// a k=3 conv read the SAME staged activation window; nothing is im2col-copied.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "conv_f32.cuh"
+#include "fsvc_internal.h"
+
+namespace fsvc {
+
+// ---- PTX wrappers ----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate); issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives once every previously issued tcgen05.mma of this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns: thread i of the warp gets row (lane_base + i).
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (between the two 8-channel halves of a K=16 slice) |
+// [32,46) SBO>>4 (between 8-row groups) | [46,48) version=1 | [61,64) layout=0 (SWIZZLE_NONE).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9,
+// 10-12 = 1), both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// fp32 packed [C_in][K][C_out]  ->  TcW layout (hi/lo bf16, zero padded).
+__global__ void pack_tc_weights_kernel(const float* __restrict__ src, int C_in, int C_out, int K, int CIB, int n_blk,
+                                       int N_tile, int n_ntiles, __nv_bfloat16* __restrict__ dst) {
+  const size_t half = (size_t)K * CIB * N_tile;  // one (n_tile, blk, split) chunk
+  const size_t total = (size_t)n_ntiles * n_blk * half;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int e = r % 8; r /= 8;
+    const int n = r % N_tile; r /= N_tile;
+    const int g = r % (CIB / 8); r /= (CIB / 8);
+    const int k = r % K; r /= K;
+    const int blk = r % n_blk; r /= n_blk;
+    const int nt = (int)r;
+    const int ci = blk * CIB + g * 8 + e, co = nt * N_tile + n;
+    float v = 0.f;
+    if (ci < C_in && co < C_out) v = src[((size_t)ci * K + k) * C_out + co];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const size_t base = ((size_t)(nt * n_blk + blk) * 2) * half + (((size_t)k * (CIB / 8) + g) * N_tile + n) * 8 + e;
+    dst[base] = hi;
+    dst[base + half] = lo;
+  }
+}
+
+}  // namespace fsvc

@@ -248,6 +248,7 @@ class FastSVCGenerator(nn.Module):
         self._handle = None
         self._handle_device = None
         self._weights_key = None
+        self._weights_epoch = 0     # bumped whenever new weights are pushed into the library (autograd.py checks it)
         self._ws = _Workspace()
 
     # ---- weight norm (fastsvc.py:342-362) ----
@@ -292,16 +293,13 @@ class FastSVCGenerator(nn.Module):
     def _sync_weights(self, handle, device):
         """Push effective weights to the library when any parameter changed
         (optimizer step, load_state_dict, remove/apply_weight_norm, .to())."""
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = self._param_key()
         if key == self._weights_key:
             return
+        from .autograd import effective_weights
         tensors = []
         with torch.no_grad():
-            for name in handle.weight_names:
-                path, kind = name.rsplit(".", 1)
-                mod = self.get_submodule(path)
-                t = mod.bias if kind == "bias" else (mod.weight if isinstance(mod, nn.Linear)
-                                                     else effective_weight(mod))
+            for name, t in zip(handle.weight_names, effective_weights(self, handle)):
                 if t.device != device:
                     raise RuntimeError(f"parameter {name} is on {t.device}, inputs on {device}")
                 tensors.append(_f32c(t))
@@ -310,6 +308,10 @@ class FastSVCGenerator(nn.Module):
                 raise RuntimeError(f"parameter {name} has {t.numel()} elements, library expects {n}")
         handle.set_weights([t.data_ptr() for t in tensors], _stream(device))
         self._weights_key = key
+        self._weights_epoch += 1
+
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _mode(self):
         try:
@@ -417,6 +419,7 @@ class FastSVCGenerator(nn.Module):
         state["_handle"] = None
         state["_handle_device"] = None
         state["_weights_key"] = None
+        state["_weights_epoch"] = 0
         state["_ws"] = _Workspace()
         return state
 

@@ -34,9 +34,11 @@ def _check(name, grads, want):
 
 def _inputs(cs):
     from svcc23_fastsvc_b200 import synthetic as syn
-    params = syn.make_params(cs["config"], seed=cs["wseed"])
+    params = syn.make_params(cs["config"], seed=cs["wseed"], weight_norm=cs.get("weight_norm", False))
     ins = syn.make_inputs(cs["B"], cs["frames"], cs["config"], seed=cs["iseed"], with_spk=cs["with_spk"])
-    w = np.random.RandomState(cs["iseed"] + 1000).standard_normal(size=(cs["B"], 1, cs["frames"] * 160)).astype(np.float32)
+    T = cs["frames"] * syn.hop_size(cs["config"]["upsampling_scales"])
+    w = np.random.RandomState(cs["iseed"] + 1000).standard_normal(
+        size=(cs["B"], cs["config"]["out_channels"], T)).astype(np.float32)
     return params, ins, w
 
 
@@ -47,7 +49,7 @@ def test_oracle_gradients_match_reference(name):
     params, ins, w = _inputs(cs)
     tp = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in params.items()}
     args = [None if a is None else torch.from_numpy(a) for a in ins]
-    y = otorch.generator_forward(tp, *args, recompute=True)
+    y = otorch.generator_forward(tp, *args, cs["config"]["upsampling_scales"], recompute=True)
     loss = (y * torch.from_numpy(w)).sum()
     assert abs(float(loss.detach()) - cs["loss"]) <= 1e-4 * max(1.0, abs(cs["loss"]))
     loss.backward()
@@ -63,14 +65,15 @@ def test_cuda_generator_gradients_match_reference(name):
     params, ins, w = _inputs(cs)
     dev = torch.device("cuda:0")
     g = M.FastSVCGenerator(**{k: (list(v) if isinstance(v, list) else v) for k, v in cs["config"].items()})
-    g.remove_weight_norm()
+    if not cs.get("weight_norm", False):
+        g.remove_weight_norm()
     g.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
     g = g.train().to(dev)
     args = [None if a is None else torch.from_numpy(a).to(dev) for a in ins]
     y = g(*args)
     assert y.requires_grad
     loss = (y * torch.from_numpy(w).to(dev)).sum()
-    assert abs(float(loss.detach()) - cs["loss"]) <= 2e-3 * cs["B"] * cs["frames"] * 160 * 0.05 + 1e-3   # forward within 1e-3 per sample
+    assert abs(float(loss.detach()) - cs["loss"]) <= 2e-3 * w.size * 0.05 + 1e-3   # forward within 1e-3 per sample
     loss.backward()
     grads = {k: p.grad.cpu().numpy() for k, p in g.named_parameters() if p.grad is not None}
     _check(name, grads, cs["grads"])
