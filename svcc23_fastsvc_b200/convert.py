@@ -102,7 +102,8 @@ class BatchConverter:
     ``sampling_rate``; ``max_batch`` utterances per launch.
     """
 
-    def __init__(self, generator, signal_generator, sampling_rate=16000, max_batch=32):
+    def __init__(self, generator, signal_generator, sampling_rate=16000, max_batch=32, writer_threads=0):
+        self.writer_threads = writer_threads   # convert_to_dir: wav files written by a small thread pool (0 = inline)
         self.g = generator
         self.sg = signal_generator
         self.sampling_rate = sampling_rate
@@ -217,5 +218,17 @@ class BatchConverter:
     def convert_to_dir(self, utterances, outdir, suffix="_gen", **kw):
         """decode_fastsvc.py:193-198: one ``{utt_id}{suffix}.wav`` (PCM-16) per utterance."""
         os.makedirs(outdir, exist_ok=True)
-        self.convert(utterances, sink=lambda uid, pcm: write_wav(os.path.join(outdir, f"{uid}{suffix}.wav"), pcm,
-                                                                 self.sampling_rate), **kw)
+
+        def write(uid, pcm):
+            write_wav(os.path.join(outdir, f"{uid}{suffix}.wav"), pcm, self.sampling_rate)
+
+        if self.writer_threads <= 0:
+            self.convert(utterances, sink=write, **kw)
+            return
+        # file writing releases the GIL: a few threads keep it off the packing / launching thread
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=self.writer_threads) as pool:
+            futures = []
+            self.convert(utterances, sink=lambda uid, pcm: futures.append(pool.submit(write, uid, pcm)), **kw)
+            for f in futures:
+                f.result()

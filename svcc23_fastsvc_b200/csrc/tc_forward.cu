@@ -370,7 +370,9 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
       if (level_fused_fill_desc(&fa) != 0) return fail(FSVC_E_INVALID, "internal: fused level descriptor table overflow");
       launch_pdl(level0_fused_kernel, dim3(grid), kLfThreads, LF.total, stream, fa);
       const double BT = (double)B * T_l;
-      c.launched("fused_level", 2.0 * BT * C * (2.0 * (3 + 1 + 9.0 * C) + 2.0 * 9 * C + 12.0 * C),
+      // both branches: first conv (3) + 1x1 residual (1) + d2, d4, FiLM conv (9C) MACs per channel and step; merged
+      // film_out: 2C -> 2C, k = 3 (12C per channel); SURVEY 8d: 17.9 GFLOP at B = 32, C = 24, T = 16000
+      c.launched("fused_level", 2.0 * BT * C * (2.0 * (3 + 1 + 9.0 * C) + 12.0 * C),
                  4.0 * (2 * BT + 2 * BT * C / dec + 2 * BT * C));
       fused_l0 = true;
       T_prev = T_l;

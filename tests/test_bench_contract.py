@@ -8,7 +8,7 @@ from conftest import REPO
 
 
 def test_reference_arm_prints_one_contract_line():
-    env = dict(os.environ, OMP_NUM_THREADS="4")
+    env = dict(os.environ, OMP_NUM_THREADS="1")     # what torchrun exports: the arm must still use every core
     res = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env, cwd=REPO)
     assert res.returncode == 0, res.stderr[-2000:]
@@ -20,7 +20,20 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "configs[1]" in d["config"]["workload"]
+    assert "configs[1]" in d["config"]["workload"] and "bounded" not in d["config"]["workload"]   # the whole batch of 32
+    assert d["cpu_baseline"]["cores"] == os.cpu_count() and d["cpu_baseline"]["cpu_model"]
+    assert abs(d["value"] - 32 * 16000 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+
+
+def test_reference_arm_train_and_convert_configs():
+    for cfg, extra in (("train", []), ("convert", ["--ref-utts", "2"])):
+        res = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--config", cfg,
+                              "--steps", "1", "--warmup", "1"] + extra, capture_output=True, text=True, timeout=900,
+                             cwd=REPO)
+        assert res.returncode == 0, res.stderr[-2000:]
+        d = json.loads([l for l in res.stdout.splitlines() if l.strip()][-1])
+        assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+        assert d["e2e"]["value"] == d["value"] and f"configs[{2 if cfg == 'train' else 4}]" in d["config"]["workload"]
 
 
 def test_reference_arm_is_rank0_only():

@@ -19,6 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--frames", type=int, default=51)
 ap.add_argument("--no-eager", action="store_true")
+ap.add_argument("--once", action="store_true", help="two steps only (what an ncu launch-list pass wraps)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 cfg = dict(syn.YAML_CONFIG)
@@ -49,6 +50,11 @@ def timed(fn, n=10, warm=3):
     return e0.elapsed_time(e1) / n
 
 
+if args.once:
+    step()
+    step()
+    torch.cuda.synchronize()
+    sys.exit(0)
 ms = timed(step)
 print(f"native fwd+bwd B={args.batch} frames={args.frames}: {ms:.3f} ms/step, launches fwd+bwd (last call) {g.last_launch_count()}")
 with torch.no_grad():
