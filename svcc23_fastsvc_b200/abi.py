@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsvc.so")
+LIB_PATH = os.environ.get("FSVC_LIB") or os.path.join(_HERE, "libfsvc.so")   # FSVC_LIB: a debug build (timeline)
 MAX_STAGES = 8
 
 MODE_FP32 = 0

@@ -49,24 +49,29 @@ def _run(cmd, verbose):
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, timeline=False):
+    """timeline=True builds libfsvc_tl.so with -DFSVC_TIMELINE (in-kernel event stamps, tools/timeline.py; select it
+    with FSVC_LIB=.../libfsvc_tl.so)."""
     sources = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     hdrs = _headers()
-    objs = [os.path.join(OBJ, s[:-3] + ".o") for s in sources]
-    if not force and os.path.exists(OUT) and not _newer(OUT, hdrs + [os.path.join(CSRC, s) for s in sources]):
-        return OUT   # a shipped .so (the GPU box gets no build/ directory it could compare against)
-    os.makedirs(OBJ, exist_ok=True)
+    out = OUT.replace("libfsvc.so", "libfsvc_tl.so") if timeline else OUT
+    objdir = OBJ + "_tl" if timeline else OBJ
+    objs = [os.path.join(objdir, s[:-3] + ".o") for s in sources]
+    if not force and os.path.exists(out) and not _newer(out, hdrs + [os.path.join(CSRC, s) for s in sources]):
+        return out   # a shipped .so (the GPU box gets no build/ directory it could compare against)
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
+    flags = NVCC_FLAGS + (["-DFSVC_TIMELINE"] if timeline else [])
     todo = []
     for s, o in zip(sources, objs):
         src = os.path.join(CSRC, s)
         if force or _newer(o, hdrs + [src]):
-            todo.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", o, src])
+            todo.append([nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", o, src])
     with ThreadPoolExecutor(max_workers=max(1, len(todo))) as ex:
         list(ex.map(lambda c: _run(c, verbose), todo))
-    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs, verbose)
-    return OUT
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs, verbose)
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timeline="--timeline" in sys.argv))

@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fsvc_internal.h"
+
 namespace fsvc {
 
 struct ConvArgs {
@@ -241,29 +243,45 @@ static __global__ void spk_project_kernel(const float* __restrict__ spk, int S, 
   }
 }
 
-// PyTorch (Cout, Cin, K) -> packed [ci_off + ci][k][co_off + co] with row length dst_cout.
+// PyTorch (Cout, Cin, K) -> packed [ci_off + ci][k][co_off + co] with row length dst_cout (block-level entry points,
+// which get their weights per call; the generator's weights go through weight_jobs_kernel).
 static __global__ void repack_weight_kernel(const float* __restrict__ src, int C_out, int C_in, int K,
-                                     float* __restrict__ dst, int dst_cout, int ci_off, int co_off) {
+                                            float* __restrict__ dst, int dst_cout, int ci_off, int co_off) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C_out * C_in * K) return;
   const int k = i % K, ci = (i / K) % C_in, co = i / (K * C_in);
   dst[((long long)(ci_off + ci) * K + k) * dst_cout + co_off + co] = src[i];
 }
 
-// packed [C_in][K][C_out] -> packed [C_out][K][C_in] with the taps reversed: the conv whose output is the gradient of
-// the original conv's input (dgrad):  g_in[u] = sum_{k,co} W[co,ci,k] * g_out[u - (k-(K-1)/2)*dil].
-static __global__ void transpose_weight_kernel(const float* __restrict__ w, int C_in, int C_out, int K, float* __restrict__ wT) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= C_out * C_in * K) return;
-  const int co = i % C_out, k = (i / C_out) % K, ci = i / (C_out * K);
-  wT[((long long)co * K + (K - 1 - k)) * C_in + ci] = w[i];
-}
-
 // dst[off + i] = a[i] (+ b[i])
 static __global__ void bias_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, int n,
-                                float* __restrict__ dst, int off) {
+                                       float* __restrict__ dst, int off) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[off + i] = a[i] + (b ? b[i] : 0.f);
+}
+
+// Weight preparation, batched: job blockIdx.y of the table, elements strided over blockIdx.x (fsvc_internal.h: WJob).
+//   0 repack     PyTorch (Cout, Cin, K) -> packed [ci_off + ci][k][co_off + co] with row length dst_ld
+//   1 bias       dst[co_off + i] = a[i] (+ b[i])
+//   2 copy       dst[i] = a[i]
+//   3 transpose  packed [C_in][K][C_out] -> packed [C_out][K][C_in] with the taps reversed: the conv whose output is
+//                the gradient of the original conv's input:  g_in[u] = sum_{k,co} W[co,ci,k] * g_out[u - (k-(K-1)/2)*dil]
+static __global__ void __launch_bounds__(256) weight_jobs_kernel(const WJob* __restrict__ jobs, const WSrc src) {
+  const WJob j = jobs[blockIdx.y];
+  float* dst = reinterpret_cast<float*>(j.dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.total; i += (long long)gridDim.x * blockDim.x) {
+    if (j.kind == 0) {
+      const int k = (int)(i % j.K), ci = (int)((i / j.K) % j.C_in), co = (int)(i / ((long long)j.K * j.C_in));
+      dst[((long long)(j.ci_off + ci) * j.K + k) * j.dst_ld + j.co_off + co] = src.p[j.src_a][i];
+    } else if (j.kind == 1) {
+      dst[j.co_off + i] = src.p[j.src_a][i] + (j.src_b >= 0 ? src.p[j.src_b][i] : 0.f);
+    } else if (j.kind == 2) {
+      dst[i] = src.p[j.src_a][i];
+    } else {
+      const int co = (int)(i % j.C_out), k = (int)((i / j.C_out) % j.K), ci = (int)(i / ((long long)j.C_out * j.K));
+      dst[((long long)co * j.K + (j.K - 1 - k)) * j.C_in + ci] = j.w[i];
+    }
+  }
 }
 
 }  // namespace fsvc

@@ -131,6 +131,20 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// wait until at most `n` of this thread's cp.async groups are still pending (n is a run-time value, 0..8)
+__device__ __forceinline__ void cp_async_wait_n(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    case 7: cp_async_wait<7>(); break;
+    default: cp_async_wait<8>(); break;
+  }
+}
 // bf16 hi|lo split of 8 fp32 values into two packed 16-byte chunks
 __device__ __forceinline__ void split_bf16(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h4[4], l4[4];
@@ -201,11 +215,16 @@ enum {  // mbarrier indices
   kBarAccFull = 10,  // [2] accumulator holds a finished tile
   kBarAccEmpty = 12, // [2] epilogue drained it
   kBarWFull = 14,    // resident weights landed
-  kBarCount = 15
+  kBarStgFull = 15,  // [4] bulk-copied raw rows of a staging slot landed (lean transform, MODE 3 / 4)
+  kBarStgEmpty = 19, // [4] every transform warp has converted the slot's rows
+  kBarCount = 23
 };
 
 // Shared-memory plan of one launch.  Returns false when even a 1-deep A ring does not fit.
-__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool small = false, int cpw_force = 0) {
+// cpw_force = 4 / 6: lean transform (MODE 3 / 4 / 5).  bulk = true (MODE 3 / 4): a staging slot holds the 6 aligned
+// 32-row blocks of the input that cover an item's window, filled by cp.async.bulk.
+__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool small = false, int cpw_force = 0,
+                                   bool bulk = false) {
   const int halo = (K / 2) * a.dil, W = kTc2M + 2 * halo;
   const uint32_t Gb = a.CIB / 8;
   c->a_bytes = 2u * Gb * W * 16u;
@@ -239,6 +258,7 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
     c->cpw = cpw_force ? cpw_force : pr[2];
     if (cpw_force && pr[2] != 4) continue;
     c->stg_bytes = a.gen_w ? 0u : xw * (uint32_t)c->cpw * 1024u;
+    if (bulk) c->stg_bytes = 6u * (uint32_t)(a.CIB >> 2) * 512u;
     uint32_t off = 0;
     c->off_w = off;
     off += w_bytes;
@@ -316,6 +336,10 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       mbar_init(bars + kBarAEmpty + i, 1);
     }
     mbar_init(bars + kBarWFull, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bars + kBarStgFull + i, 1);
+      mbar_init(bars + kBarStgEmpty + i, SH::kXW);
+    }
     fence_barrier_init();
   }
   if (warp == SH::kMmaWarp) tmem_alloc(s_tmem, 2 * acc_stride);
@@ -330,29 +354,68 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   const int co_tile = nt * a.N_tile;
 
   if (warp == 0 && lane == 0) {
-    // =============================== WEIGHTS ===============================
-    {
-      const uint8_t* w_nt =
-          reinterpret_cast<const uint8_t*>(a.w + prob * L.d_w) + (size_t)nt * a.n_blk * c.b_bytes;
-      if (a.w_resident) {
-        const uint32_t total = c.b_bytes * a.n_blk;
-        mbar_expect_tx(bars + kBarWFull, total);
-        for (uint32_t o = 0; o < total; o += 32768u)
-          bulk_g2s(smem + c.off_w + o, w_nt + o, min(32768u, total - o), bars + kBarWFull);
-      } else {
-        uint32_t pbk = 0;
-        for (int m = first; m < n_m; m += step) {
-          for (int blk = 0; blk < a.n_blk; ++blk, ++pbk) {
-            const uint32_t slot = pbk & 1u, use = pbk >> 1;
-            if (use > 0) mbar_wait2(bars + kBarBEmpty + slot, (use + 1) & 1u);
-            mbar_expect_tx(bars + kBarBFull + slot, c.b_bytes);
-            const uint8_t* src = w_nt + (size_t)blk * c.b_bytes;
-            uint8_t* dst = smem + c.off_b + slot * c.b_bytes;
-            for (uint32_t o = 0; o < c.b_bytes; o += 32768u)
-              bulk_g2s(dst + o, src + o, min(32768u, c.b_bytes - o), bars + kBarBFull + slot);
+    // =============================== WEIGHTS (+ ROW LOADER of the lean transform) ===============================
+    const uint8_t* w_nt = reinterpret_cast<const uint8_t*>(a.w + prob * L.d_w) + (size_t)nt * a.n_blk * c.b_bytes;
+    if (a.w_resident) {
+      const uint32_t total = c.b_bytes * a.n_blk;
+      mbar_expect_tx(bars + kBarWFull, total);
+      for (uint32_t o = 0; o < total; o += 32768u)
+        bulk_g2s(smem + c.off_w + o, w_nt + o, min(32768u, total - o), bars + kBarWFull);
+    }
+    uint32_t pbk = 0;
+    auto stream_weights = [&](int blk) {  // one (N tile, ci block) chunk into the 2-slot ring
+      const uint32_t slot = pbk & 1u, use = pbk >> 1;
+      if (use > 0) mbar_wait2(bars + kBarBEmpty + slot, (use + 1) & 1u);
+      mbar_expect_tx(bars + kBarBFull + slot, c.b_bytes);
+      const uint8_t* src = w_nt + (size_t)blk * c.b_bytes;
+      uint8_t* dst = smem + c.off_b + slot * c.b_bytes;
+      for (uint32_t o = 0; o < c.b_bytes; o += 32768u)
+        bulk_g2s(dst + o, src + o, min(32768u, c.b_bytes - o), bars + kBarBFull + slot);
+      ++pbk;
+    };
+    if constexpr (MODE == 3 || MODE == 4) {
+      // The blocked channels-last layout keeps the channels of 32 consecutive time steps contiguous, so the <= 6
+      // aligned 32-row blocks covering an item's window [t0 - halo, t0 + 128 + halo) are, per ci block, <= 6 bulk
+      // copies (TMA engine) into one staging slot, completed on the slot's mbarrier.  They are issued from this
+      // thread: measured from inside the transform role, issuing an item's copies cost 0.7 us on its critical path.
+      const float4* in4 = reinterpret_cast<const float4*>(a.in + prob * L.d_in);
+      const long long Tp_in = ntc_tp(a.T_in), ld4 = a.in_ld >> 2;
+      const uint32_t row_bytes = (uint32_t)(a.CIB >> 2) * 512u;  // one staged 32-row block of a ci block
+      const int n_blk32 = (int)(Tp_in >> 5), ring = c.stg_depth + 1;
+      int lb = first / c.m_tiles, ltile = first - lb * c.m_tiles;
+      uint32_t slot = 0, use = 0;
+      bool waited = false;
+      for (int m = first; m < n_m; ++m) {
+        const int r0 = ltile * (kTc2M / 32) - 1;  // first staged block (-1 at the start of an utterance: not copied)
+        int nv = 0;
+        for (int r = 0; r < 6; ++r) nv += (r0 + r >= 0 && r0 + r < n_blk32) ? 1 : 0;
+        for (int blk = 0; blk < a.n_blk; ++blk) {
+          if (!a.w_resident) stream_weights(blk);
+          if (!waited) {
+            griddep_wait();  // first access to the predecessor's output (the weights above do not depend on it)
+            waited = true;
+          }
+          if (use > 0) mbar_wait2(bars + kBarStgEmpty + slot, (use + 1) & 1u);
+          const uint32_t nbytes = (uint32_t)(min(a.CIB, a.C_in - blk * a.CIB) >> 2) * 512u;  // real channels of the block
+          uint64_t* bar = bars + kBarStgFull + slot;
+          mbar_expect_tx(bar, (uint32_t)nv * nbytes);
+          uint8_t* dst = smem + c.off_stg + slot * c.stg_bytes;
+          const float4* src = in4 + ((long long)lb * Tp_in + (long long)r0 * 32) * ld4 + (long long)blk * (a.CIB >> 2) * 32;
+          for (int r = 0; r < 6; ++r)
+            if (r0 + r >= 0 && r0 + r < n_blk32) bulk_g2s(dst + (uint32_t)r * row_bytes, src + (long long)r * 32 * ld4, nbytes, bar);
+          if (++slot == (uint32_t)ring) {
+            slot = 0;
+            ++use;
           }
         }
+        if (++ltile == c.m_tiles) {
+          ltile = 0;
+          ++lb;
+        }
       }
+    } else if (!a.w_resident) {
+      for (int m = first; m < n_m; m += step)
+        for (int blk = 0; blk < a.n_blk; ++blk) stream_weights(blk);
     }
   }
   if (warp == SH::kMmaWarp) {
@@ -379,8 +442,10 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         if (it >= 2) mbar_wait2(bars + kBarAccEmpty + acc, (((uint32_t)it >> 1) + 1) & 1u);
         const uint32_t d_tmem = tmem_u + acc * acc_stride;
         for (int blk = 0; blk < a.n_blk; ++blk) {
+          if (leader && it == 5 && blk == 0) FSVC_TL(L.tl_slot, 51);
           mbar_wait2(bars + kBarAFull + aslot, ause & 1u);
           if (leader && it == 0 && blk < 12) FSVC_TL(L.tl_slot, 20 + blk);
+          if (leader && it == 5 && blk == 0) FSVC_TL(L.tl_slot, 52);
           uint32_t sB_addr;
           const uint32_t bslot = pbk & 1u;
           if (a.w_resident) {
@@ -414,6 +479,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             if (!a.w_resident) umma_commit(bars + kBarBEmpty + bslot);
             if (blk == a.n_blk - 1) umma_commit(bars + kBarAccFull + acc);
             if (it == 0 && blk == a.n_blk - 1) FSVC_TL(L.tl_slot, 36);
+            if (it == 5 && blk == a.n_blk - 1) FSVC_TL(L.tl_slot, 53);
           }
           if (!a.w_resident) ++pbk;
           if (++aslot == (uint32_t)c.a_slots) {
@@ -888,62 +954,34 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     // registers; per item a task costs its address add, one bounds compare, two copies / two loads, the arithmetic
     // and two predicated stores.
     constexpr int NT = MODE == 4 ? 6 : 4;
-    int goff[NT], rel[NT];
-    uint32_t soff[NT], aoff[NT], flags[NT];  // flags: bit 0 = task exists, bit 1 = this lane's row is inside the window
+    // Raw rows arrive by bulk copy (row loader in warp 0): per (item, ci block) a staging slot holds the <= 6 aligned
+    // 32-row blocks covering the window -- the transform warps issue no loads and compute no global addresses.
+    // Everything below the block index is tile- and block-invariant and lives in registers.
+    int rel[NT];
+    uint32_t stoff[NT], soff[NT], aoff[NT], flags[NT];  // flags: bit 0 = task exists, bit 1 = lane's row is in the window
+    int gch[NT];                                        // first channel of the task's group inside its ci block
+    const uint32_t row_bytes = (uint32_t)(a.CIB >> 2) * 512u;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const int k = xw + j * SH::kXW;
       const int g = k / nseg, seg = k - g * nseg;
-      const bool on = k < ntask && g * 8 < a.C_in;  // (channel padding groups are zero-filled once, below)
-      goff[j] = (int)(seg * 32 * ld4) + g * 64;
+      const bool on = k < ntask;
       rel[j] = seg * 32 + hl;
+      const int w32 = 32 + seg * 32 + hl;           // window row of this lane, counted from the first staged block
+      stoff[j] = (uint32_t)(w32 >> 5) * row_bytes + (uint32_t)(2 * g) * 512u + (uint32_t)(w32 & 31) * 16u;
       soff[j] = (uint32_t)g * strip + (uint32_t)seg * 512u + (uint32_t)lane * 16u;
       aoff[j] = (uint32_t)g * 32u;
+      gch[j] = g * 8;
       flags[j] = (on ? 1u : 0u) | ((on && seg * 32 + lane < W) ? 2u : 0u);
     }
-    // channel-padding groups of the (single) ci block never change: zero them in every A slot once
-    for (int sl = 0; sl < c.a_slots; ++sl)
-      for (int idx = tt; idx < Gb * W; idx += kTc3XformThreads) {
-        const int g = idx / W, rw = idx - g * W;
-        if (g * 8 >= a.C_in) {
-          const uint32_t d = smem_base + c.off_a + (uint32_t)sl * c.a_bytes + (uint32_t)g * strip + (uint32_t)rw * 16u;
-          sts128(d, make_uint4(0u, 0u, 0u, 0u));
-          sts128(d + plane, make_uint4(0u, 0u, 0u, 0u));
-        }
-      }
-    const int depth = c.stg_depth;
+    const int depth = c.stg_depth;  // ring of depth + 1 staging slots, one full / empty mbarrier pair each
     const uint32_t sA0 = smem_base + c.off_a, s_pa0 = smem_base + c.off_pa;
     const uint32_t pa_stride = (uint32_t)(2 * cpad) * 4u, pc_off = (uint32_t)cpad * 4u;
-    griddep_wait();  // first access to the predecessor's output
+    const uint32_t stg_base = smem_base + c.off_stg;
     if (tt == 0) FSVC_TL(L.tl_slot, 2);
-    // item cursors: `a*` = item whose copies are issued next, `c*` = item converted next
-    int am = first, ab = first / c.m_tiles, atile = first - ab * c.m_tiles;
-    int cm = first, cb = ab, ctile = atile, it = 0;
-    uint32_t slot_i = 0, slot_c = 0, aslot = 0, ause = 0, pa_buf = 0;
-    auto issue = [&]() {
-      if (am < n_m) {
-        const int t0 = atile * kTc2M;
-        const float4* tb = in4 + ((long long)ab * Tp_in + t0) * ld4 + thr_goff;
-        const uint32_t dst0 = stg0 + slot_i * c.stg_bytes;
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          if (flags[j] & 1u) {  // warp-uniform, loop-invariant
-            const bool ok = (flags[j] & 2u) && (unsigned)(t0 + rel[j]) < (unsigned)a.T_out;
-            const float4* p = ok ? tb + goff[j] : in4;
-            cp_async16(dst0 + (uint32_t)j * 1024u, p, ok ? 16u : 0u);
-            cp_async16(dst0 + (uint32_t)j * 1024u + 512u, p + (ok ? 32 : 0), ok ? 16u : 0u);
-          }
-        }
-        ++am;
-        if (++atile == c.m_tiles) {
-          atile = 0;
-          ++ab;
-        }
-      }
-      cp_async_commit();
-      slot_i = slot_i == (uint32_t)depth ? 0u : slot_i + 1u;
-    };
-    for (int i = 0; i < depth; ++i) issue();
+    int cm = first, cb = first / c.m_tiles, ctile = first - cb * c.m_tiles, it = 0;
+    uint32_t slot_c = 0, use_c = 0, aslot = 0, ause = 0, pa_buf = 0;
+    if (has_aff) griddep_wait();  // the affine below reads the predecessor's statistics
     if (cm < n_m) update_affine(Cursor{cm, 0, 0, 0, cb, ctile});
     while (cm < n_m) {
       // affine of the next item's utterance, one item ahead (as in the other modes)
@@ -952,61 +990,77 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         ntile = 0;
         ++nb;
       }
+      if (tt == 0 && it == 5) FSVC_TL(L.tl_slot, 41);
       if (cm + 1 < n_m) update_affine(Cursor{cm + 1, 0, 0, it + 1, nb, ntile});
-      if (depth == 3) cp_async_wait<2>();
-      else if (depth == 2) cp_async_wait<1>();
-      else cp_async_wait<0>();
-      if (tt == 0 && it == 0) FSVC_TL(L.tl_slot, 3);
-      if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
       if (has_aff && cb != cv_b) {  // new utterance: its affine was written one item ago
         cv_b = cb;
         pa_buf = pa_buf == 2 ? 0 : pa_buf + 1;
         named_bar_sync(1, kTc3XformThreads);
       }
-      {
-        const uint32_t sA = sA0 + aslot * c.a_bytes;
-        const uint32_t s_pa = s_pa0 + pa_buf * pa_stride, s_pc = s_pa + pc_off;
-        const uint32_t src0 = stg0 + slot_c * c.stg_bytes;
-        const int t0 = ctile * kTc2M;
+      const int t0 = ctile * kTc2M;
+      for (int blk = 0; blk < a.n_blk; ++blk) {
+        mbar_wait2(bars + kBarStgFull + slot_c, use_c & 1u);
+        if (tt == 0 && it == 0 && blk == 0) FSVC_TL(L.tl_slot, 3);
+        if (tt == 0 && it == 5 && blk == 0) FSVC_TL(L.tl_slot, 42);
+        if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
+        if (tt == 0 && it == 5 && blk == 0) FSVC_TL(L.tl_slot, 43);
+        {
+          const uint32_t sA = sA0 + aslot * c.a_bytes;
+          const uint32_t s_pa = s_pa0 + pa_buf * pa_stride + (uint32_t)(blk * a.CIB) * 4u, s_pc = s_pa + pc_off;
+          const uint32_t src0 = stg_base + slot_c * c.stg_bytes;
+          const int c_left = a.C_in - blk * a.CIB;  // real channels from this block on
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          if (flags[j] & 1u) {
-            const float4 dA = lds128f(src0 + (uint32_t)j * 1024u), dB = lds128f(src0 + (uint32_t)j * 1024u + 512u);
-            float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
-            if (has_aff) {
-              const float4 a0 = lds128f(s_pa + aoff[j]), a1 = lds128f(s_pa + aoff[j] + 16u);
-              const float4 c0 = lds128f(s_pc + aoff[j]), c1 = lds128f(s_pc + aoff[j] + 16u);
-              v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
-              v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
-              v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
-              v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
-            }
-            if (a.pre_lrelu) {
+          for (int j = 0; j < NT; ++j) {
+            if (flags[j] & 1u) {
+              // rows outside the utterance and channel padding are zero AFTER the prologue (their staging bytes may
+              // be stale: never used)
+              const uint32_t in_strip = (flags[j] >> 1) & 1u;
+              const uint32_t real = ((unsigned)(t0 + rel[j]) < (unsigned)a.T_out && gch[j] < c_left) ? 1u : 0u;
+              float4 dA = make_float4(0.f, 0.f, 0.f, 0.f), dB = dA;
+              if (in_strip & real) {
+                dA = lds128f(src0 + stoff[j]);
+                dB = lds128f(src0 + stoff[j] + 512u);
+              }
+              float v[8] = {dA.x, dA.y, dA.z, dA.w, dB.x, dB.y, dB.z, dB.w};
+              if (has_aff) {
+                const float4 a0 = lds128f(s_pa + aoff[j]), a1 = lds128f(s_pa + aoff[j] + 16u);
+                const float4 c0 = lds128f(s_pc + aoff[j]), c1 = lds128f(s_pc + aoff[j] + 16u);
+                v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
+                v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
+                v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
+                v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+              }
+              if (a.pre_lrelu) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
+              }
+              split_store_p(sA + soff[j], plane, v, in_strip & real, in_strip & ~real);
             }
-            // rows outside the utterance are zero AFTER the prologue
-            const uint32_t in_strip = (flags[j] >> 1) & 1u;
-            const uint32_t real = (unsigned)(t0 + rel[j]) < (unsigned)a.T_out ? 1u : 0u;
-            split_store_p(sA + soff[j], plane, v, in_strip & real, in_strip & ~real);
           }
         }
+        if (tt == 0 && it == 5 && blk == 0) FSVC_TL(L.tl_slot, 44);
+        fence_proxy_async();
+        mbar_arrive(bars + kBarAFull + aslot);
+        if (tt == 0 && (a.n_blk == 1 ? it : blk) < 12 && (a.n_blk == 1 || it == 0)) FSVC_TL(L.tl_slot, 4 + (a.n_blk == 1 ? it : blk));
+        if (++aslot == (uint32_t)c.a_slots) {
+          aslot = 0;
+          ++ause;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + kBarStgEmpty + slot_c);  // this warp is done with the slot's rows
+        if (slot_c == (uint32_t)depth) {
+          slot_c = 0;
+          ++use_c;
+        } else {
+          ++slot_c;
+        }
       }
-      fence_proxy_async();
-      mbar_arrive(bars + kBarAFull + aslot);
-      if (tt == 0 && it < 12) FSVC_TL(L.tl_slot, 4 + it);
-      if (++aslot == (uint32_t)c.a_slots) {
-        aslot = 0;
-        ++ause;
-      }
-      slot_c = slot_c == (uint32_t)depth ? 0u : slot_c + 1u;
-      issue();
+      if (tt == 0 && it == 5) FSVC_TL(L.tl_slot, 47);
       ++cm;
       ++it;
       cb = nb;
       ctile = ntile;
     }
-    cp_async_wait<0>();
    } else if constexpr (MODE == 2) {
     // ---- MODE 2: nearest-repeat input.  Window row rw <-> output-rate step u = u_lo + rw reads source row u / up,
     // so a source row s feeds the window rows of steps s*up .. s*up+up-1: load + convert it once, store it `up`
@@ -1141,9 +1195,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         Cursor nxt = cur;
         advance(nxt);
         if (nxt.m < n_m) update_affine(nxt);
-        if (depth == 3) cp_async_wait<3>();
-        else if (depth == 2) cp_async_wait<2>();
-        else cp_async_wait<1>();
+        cp_async_wait_n(depth);
         if (tt == 0 && cur.it == 0 && cur.blk == 0 && cur.ch == 0) FSVC_TL(L.tl_slot, 3);
         convert_chunk(cur, slot_c);
         slot_c = slot_c + 1 == (uint32_t)depth + 1 ? 0 : slot_c + 1;
@@ -1258,9 +1310,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         Cursor nxt = cur;
         advance(nxt);
         if (nxt.m < n_m) update_affine(nxt);
-        if (depth == 3) cp_async_wait<3>();
-        else if (depth == 2) cp_async_wait<2>();
-        else cp_async_wait<1>();
+        cp_async_wait_n(depth);
         if (tt == 0 && cur.it == 0 && cur.blk == 0 && cur.ch == 0) FSVC_TL(L.tl_slot, 3);
         convert_chunk(cur, slot_c);
         slot_c = slot_c + 1 == (uint32_t)depth + 1 ? 0 : slot_c + 1;
@@ -1339,8 +1389,10 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       float* raw_row = raw ? raw + ntc_row(Tp_out, a.raw_ld, b, t) : nullptr;
       float* out_row = out ? out + ntc_row(Tp_out, a.out_ld, b, t) : nullptr;
       float2* st_row = has_stats ? a.stats + ((long long)b * a.n_seg + (t0 >> 5) + q) * a.C_out : nullptr;
+      if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 48);
       mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
       if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 38);
+      if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 49);
       tc_fence_after();
       const uint32_t tacc = tmem + acc * acc_stride + lane_addr;
       for (int sub = 0; sub < n_sub; ++sub) {
@@ -1386,6 +1438,17 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             }
             if (out_row && ok) reinterpret_cast<float4*>(out_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
             v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
+          }
+        }
+        if (a.last_w && ok) {
+          // conv_last (Conv1d1x1, fastsvc.py:301,330) on the value just produced: this thread's channels' share of every
+          // output channel; the other column half adds its share (two commutative adds onto zero: deterministic)
+          for (int o = 0; o < a.last_co; ++o) {
+            float p = (h == 0) ? __ldg(a.last_b + o) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (NH4 ? j < 4 * NH4 : j < nh) p = fmaf(v[j], __ldg(a.last_w + (long long)(co + j) * a.last_co + o), p);
+            atomicAdd(a.last_out + ((long long)b * a.last_co + o) * a.T_out + t, p);
           }
         }
         // request the next unit's operands now; they land while this thread waits for the next accumulator
@@ -1439,6 +1502,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
           }
         }
       }
+      if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 50);
       tc_fence_before();
       mbar_arrive(bars + kBarAccEmpty + acc);
       if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 39);

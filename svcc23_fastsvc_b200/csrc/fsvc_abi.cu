@@ -284,6 +284,8 @@ extern "C" {
 int fsvc_abi_version(void) { return FSVC_ABI_VERSION; }
 const char* fsvc_last_error(void) { return g_err; }
 
+static int build_weight_jobs(fsvc_handle* h);
+
 int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
   if (!cfg || !out) return fail(FSVC_E_INVALID, "null argument");
   *out = nullptr;
@@ -418,6 +420,10 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
     return rc;
   }
   tc_fix_pointers(h);
+  if (int rc = build_weight_jobs(h)) {
+    fsvc_destroy(h);
+    return rc;
+  }
   if (int rc = tc_setup_kernels()) {
     cudaFree(h->store);
     cudaFree(h->tc_store);
@@ -441,6 +447,9 @@ void fsvc_destroy(fsvc_handle* h) {
   if (!h) return;
   if (h->store) cudaFree(h->store);
   if (h->tc_store) cudaFree(h->tc_store);
+  if (h->jobs_a) cudaFree(h->jobs_a);
+  if (h->jobs_t) cudaFree(h->jobs_t);
+  if (h->jobs_tc) cudaFree(h->jobs_tc);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_ppg) cudaEventDestroy(h->ev_ppg);
   if (h->ev_side_fork) cudaEventDestroy(h->ev_side_fork);
@@ -459,16 +468,39 @@ int fsvc_weight_tensor_info(const fsvc_handle* h, int index, char* name, int nam
   return FSVC_OK;
 }
 
-int fsvc_set_weights(fsvc_handle* h, const float* const* p, int n, void* stream_) {
-  if (!h || !p) return fail(FSVC_E_INVALID, "null argument");
-  if (n != (int)h->winfo.size()) return fail(FSVC_E_INVALID, "expected %d weight tensors, got %d", (int)h->winfo.size(), n);
-  for (int i = 0; i < n; ++i)
-    if (!p[i]) return fail(FSVC_E_INVALID, "weight tensor %d (%s) is null", i, h->winfo[i].name.c_str());
-  cudaStream_t s = (cudaStream_t)stream_;
+// Device job tables of fsvc_set_weights (built once per handle; see WJob in fsvc_internal.h).
+static int build_weight_jobs(fsvc_handle* h) {
+  const int n = (int)h->winfo.size();
+  if (n > kMaxWeightTensors) return fail(FSVC_E_INVALID, "too many weight tensors (%d)", n);
+  std::vector<WJob> ja, jt;
+  auto find = [&](const std::string& name) {
+    for (int i = 0; i < n; ++i)
+      if (h->winfo[i].name == name) return i;
+    return -1;
+  };
+  auto repack_job = [&](int src, int co, int ci, int K, float* dst, int dst_ld, int ci_off, int co_off) {
+    WJob j;
+    memset(&j, 0, sizeof(j));
+    j.kind = 0; j.src_a = src; j.src_b = -1; j.C_out = co; j.C_in = ci; j.K = K;
+    j.dst = dst; j.dst_ld = dst_ld; j.ci_off = ci_off; j.co_off = co_off; j.total = (long long)co * ci * K;
+    ja.push_back(j);
+  };
+  auto bias_job = [&](int a, int b, int cnt, float* dst, int off) {
+    WJob j;
+    memset(&j, 0, sizeof(j));
+    j.kind = 1; j.src_a = a; j.src_b = b; j.dst = dst; j.co_off = off; j.total = cnt;
+    ja.push_back(j);
+  };
+  auto copy_job = [&](int a, long long cnt, float* dst) {
+    WJob j;
+    memset(&j, 0, sizeof(j));
+    j.kind = 2; j.src_a = a; j.src_b = -1; j.dst = dst; j.total = cnt;
+    ja.push_back(j);
+  };
   int k = 0;
   auto put = [&](ConvW& cw) {
-    repack(s, p[k], cw.C_out, cw.C_in, cw.K, cw.w, cw.C_out, 0, 0);
-    bias_sum(s, p[k + 1], nullptr, cw.C_out, cw.b, 0);
+    repack_job(k, cw.C_out, cw.C_in, cw.K, cw.w, cw.C_out, 0, 0);
+    bias_job(k + 1, -1, cw.C_out, cw.b, 0);
     k += 2;
   };
   const int ns = h->n;
@@ -482,9 +514,8 @@ int fsvc_set_weights(fsvc_handle* h, const float* const* p, int n, void* stream_
     put(st.res);
     if (h->cfg.use_spk_emb) {
       const int C = h->cfg.mid_channels[i];
-      FSVC_CUDA(cudaMemcpyAsync(st.emb_w, p[k], (size_t)C * h->cfg.spk_emb_size * sizeof(float),
-                                cudaMemcpyDeviceToDevice, s));
-      FSVC_CUDA(cudaMemcpyAsync(st.emb_b, p[k + 1], (size_t)C * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      copy_job(k, (long long)C * h->cfg.spk_emb_size, st.emb_w);
+      copy_job(k + 1, C, st.emb_b);
       k += 2;
     }
   }
@@ -501,33 +532,49 @@ int fsvc_set_weights(fsvc_handle* h, const float* const* p, int n, void* stream_
       LevelW& lw = h->level[l];
       put(lw.film[br]);
       // conv_scale -> output cols [0,C), conv_shift -> [C,2C); branch br reads input rows [br*C, (br+1)*C)
-      repack(s, p[k], C, C, 3, lw.film_out.w, 2 * C, br * C, 0);
-      repack(s, p[k + 2], C, C, 3, lw.film_out.w, 2 * C, br * C, C);
+      repack_job(k, C, C, 3, lw.film_out.w, 2 * C, br * C, 0);
+      repack_job(k + 2, C, C, 3, lw.film_out.w, 2 * C, br * C, C);
       k += 4;
     }
   // merged FiLM biases: gamma bias = b_scale_lft + b_scale_sine, beta bias likewise
-  {
-    // index of film_lft.l.conv_scale.bias etc. in the canonical list
-    auto find = [&](const std::string& name) {
-      for (int i = 0; i < n; ++i)
-        if (h->winfo[i].name == name) return i;
-      return -1;
-    };
-    for (int l = 0; l < ns; ++l) {
-      const int C = h->lvl_c[l];
-      const std::string sl = std::to_string(l);
-      const int a0 = find("film_lft." + sl + ".conv_scale.bias"), a1 = find("film_sine." + sl + ".conv_scale.bias");
-      const int b0 = find("film_lft." + sl + ".conv_shift.bias"), b1 = find("film_sine." + sl + ".conv_shift.bias");
-      bias_sum(s, p[a0], p[a1], C, h->level[l].film_out.b, 0);
-      bias_sum(s, p[b0], p[b1], C, h->level[l].film_out.b, C);
-    }
+  for (int l = 0; l < ns; ++l) {
+    const int C = h->lvl_c[l];
+    const std::string sl = std::to_string(l);
+    bias_job(find("film_lft." + sl + ".conv_scale.bias"), find("film_sine." + sl + ".conv_scale.bias"), C,
+             h->level[l].film_out.b, 0);
+    bias_job(find("film_lft." + sl + ".conv_shift.bias"), find("film_sine." + sl + ".conv_shift.bias"), C,
+             h->level[l].film_out.b, C);
   }
   put(h->last);
   if (k != n) return fail(FSVC_E_STATE, "internal: consumed %d of %d weight tensors", k, n);
   for (ConvW* cw : h->convs) {  // the transposed (data-gradient) copy of every conv, for the native backward
-    const int nw = cw->C_out * cw->C_in * cw->K;
-    transpose_weight_kernel<<<(nw + 255) / 256, 256, 0, s>>>(cw->w, cw->C_in, cw->C_out, cw->K, cw->wT);
+    WJob j;
+    memset(&j, 0, sizeof(j));
+    j.kind = 3; j.C_out = cw->C_out; j.C_in = cw->C_in; j.K = cw->K; j.w = cw->w; j.dst = cw->wT;
+    j.total = (long long)cw->C_out * cw->C_in * cw->K;
+    jt.push_back(j);
   }
+  h->n_jobs_a = (int)ja.size();
+  h->n_jobs_t = (int)jt.size();
+  FSVC_CUDA(cudaMalloc((void**)&h->jobs_a, ja.size() * sizeof(WJob)));
+  FSVC_CUDA(cudaMalloc((void**)&h->jobs_t, jt.size() * sizeof(WJob)));
+  FSVC_CUDA(cudaMemcpy(h->jobs_a, ja.data(), ja.size() * sizeof(WJob), cudaMemcpyHostToDevice));
+  FSVC_CUDA(cudaMemcpy(h->jobs_t, jt.data(), jt.size() * sizeof(WJob), cudaMemcpyHostToDevice));
+  return tc_build_jobs(h);
+}
+
+int fsvc_set_weights(fsvc_handle* h, const float* const* p, int n, void* stream_) {
+  if (!h || !p) return fail(FSVC_E_INVALID, "null argument");
+  if (n != (int)h->winfo.size()) return fail(FSVC_E_INVALID, "expected %d weight tensors, got %d", (int)h->winfo.size(), n);
+  for (int i = 0; i < n; ++i)
+    if (!p[i]) return fail(FSVC_E_INVALID, "weight tensor %d (%s) is null", i, h->winfo[i].name.c_str());
+  cudaStream_t s = (cudaStream_t)stream_;
+  WSrc src;
+  memset(&src, 0, sizeof(src));
+  for (int i = 0; i < n; ++i) src.p[i] = p[i];
+  // three launches: caller tensors -> packed fp32 store; packed -> transposed copies; packed -> tensor-core layouts
+  weight_jobs_kernel<<<dim3(16, h->n_jobs_a), 256, 0, s>>>(h->jobs_a, src);
+  weight_jobs_kernel<<<dim3(16, h->n_jobs_t), 256, 0, s>>>(h->jobs_t, src);
   tc_pack_weights(h, s);
   FSVC_CUDA(cudaGetLastError());
   h->weights_set = true;
@@ -789,13 +836,6 @@ int fsvc_pcm16(const float* x, int16_t* y, long long n, void* stream) {
   return FSVC_OK;
 }
 
-#ifdef FSVC_TIMELINE
-// debug builds only (tools/timeline.py): copy the event stamps of the last forward
-int fsvc_debug_timeline(unsigned long long* out, int n) {
-  FSVC_CUDA(cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * (size_t)(n < 64 * 8 * 64 ? n : 64 * 8 * 64)));
-  return FSVC_OK;
-}
-#endif
 
 int fsvc_last_launch_count(const fsvc_handle* h) { return h ? h->launches : FSVC_E_INVALID; }
 

@@ -47,6 +47,24 @@ struct ConvW {  // packed [C_in][K][C_out] + bias[C_out], device
   int nc_G = 0, nc_N = 0;
 };
 
+// One weight-preparation job.  fsvc_set_weights runs three launches over device-resident job tables built once per
+// handle (instead of ~290 tiny launches): caller tensors -> packed fp32 store (repack / bias / copy), then packed fp32
+// -> transposed copies (train.cu) and -> tensor-core bf16 hi|lo layouts (tc_forward.cu).
+struct WJob {
+  int kind;            // 0 repack, 1 bias (a [+ b]), 2 copy, 3 transpose, 4 pack_tc, 5 pack_tc_nc
+  int src_a, src_b;    // indices into the caller's pointer list (kinds 0-2); -1 = none
+  int C_out, C_in, K;
+  int dst_ld, ci_off, co_off;  // repack destination geometry
+  int CIB, n_blk, N_tile, n_ntiles, G, N;  // tensor-core layouts (kinds 4, 5)
+  const float* w;      // packed fp32 source (kinds 3-5)
+  void* dst;
+  long long total;     // elements the job loops over
+};
+constexpr int kMaxWeightTensors = 352;  // 8 stages: 14 per stage + 2 * 8 * (8 + 6) + 2
+struct WSrc {
+  const float* p[kMaxWeightTensors];
+};
+
 struct WeightInfo {
   std::string name;
   int64_t numel;
@@ -82,6 +100,10 @@ struct fsvc_handle {
   fsvc::StageW stage[FSVC_MAX_STAGES];
   fsvc::LevelW level[FSVC_MAX_STAGES];
   fsvc::ConvW last;
+  fsvc::WJob* jobs_a = nullptr;  // device job tables of fsvc_set_weights (phase A: from the caller's tensors;
+  fsvc::WJob* jobs_t = nullptr;  // transposes; tensor-core packs)
+  fsvc::WJob* jobs_tc = nullptr;
+  int n_jobs_a = 0, n_jobs_t = 0, n_jobs_tc = 0;
   bool weights_set = false;
   int launches = 0;
   int device = 0;
@@ -158,6 +180,7 @@ extern const char* const lvl_sine_label[FSVC_MAX_STAGES];
 size_t tc_plan_handle(fsvc_handle* h);
 void tc_fix_pointers(fsvc_handle* h);
 int tc_setup_kernels();
+int tc_build_jobs(fsvc_handle* h);                     // device job table of the tensor-core packs (after tc_fix_pointers)
 void tc_pack_weights(fsvc_handle* h, cudaStream_t s);  // after the fp32 packed store is filled
 size_t tc_workspace_bytes(const fsvc_handle* h, int B, int frames);
 int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk, float* out,

@@ -39,27 +39,9 @@ constexpr int kLfValid = 238;              // output steps per work item
 constexpr int kLfRows = 272;               // rows of an activation buffer (time t0-9 .. t0+262)
 constexpr int kLfHalo = 9;
 
-// fp32 packed [C_in][K][C_out]  ->  [tap][group g of 8 ci][hi: N rows | lo: N rows][8 ci] bf16 (zero padded):
-// a B descriptor over 2N rows sees [w_hi | w_lo], one over N rows sees w_hi.
-__global__ void pack_tc_nc_weights_kernel(const float* __restrict__ src, int C_in, int C_out, int K, int G, int N,
-                                          __nv_bfloat16* __restrict__ dst) {
-  const size_t total = (size_t)K * G * N * 8;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    size_t r = i;
-    const int e = r % 8; r /= 8;
-    const int n = r % N; r /= N;
-    const int g = r % G; r /= G;
-    const int k = (int)r;
-    const int ci = g * 8 + e;
-    float v = 0.f;
-    if (ci < C_in && n < C_out) v = src[((size_t)ci * K + k) * C_out + n];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    const size_t base = (((size_t)k * G + g) * 2 * N + n) * 8 + e;
-    dst[base] = hi;
-    dst[base + (size_t)N * 8] = lo;
-  }
-}
+// Weights of the fused level: fp32 packed [C_in][K][C_out]  ->  [tap][group g of 8 ci][hi: N rows | lo: N rows][8 ci]
+// bf16 (zero padded): a B descriptor over 2N rows sees [w_hi | w_lo], one over N rows sees w_hi.  Written by
+// weight_jobs_tc_kernel (tc_forward.cu, job kind 5).
 
 struct LevelFusedArgs {
   const float* sig[2];       // [B][T] raw 1-channel signals: loudness, sine

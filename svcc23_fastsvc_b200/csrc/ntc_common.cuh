@@ -51,6 +51,12 @@ struct Tc2Args {
   int out_ld;
   float2* stats;  // [B][n_seg][C_out] (mean, M2) of the stored value per 32-step segment, or nullptr
   int n_seg;
+  // conv_last folded into the epilogue (last stage only; one N tile, one sub-tile): out_last[b][o][t] (zeroed before
+  // the launch) += sum_c w_last[c][o] * v[c] over this thread's channels; exactly two contributions per sample.
+  const float* last_w;  // [C_out][last_co] fp32, or nullptr
+  const float* last_b;  // [last_co]
+  float* last_out;      // (B, last_co, T_out), time fastest
+  int last_co;
   float slope;
 };
 

@@ -35,7 +35,11 @@ static bool tc2_plan(int C_in, int C_out, int K, ConvW* cw) {
   // largest ci block whose A ring is at least double-buffered (resident weights first); else anything that fits
   int best_cib = 0, best_res = 0, fb_cib = 0, fb_res = 0;
   const int nat_blk = (c16 + 63) / 64;
-  const int nat_cib = ((c16 + nat_blk - 1) / nat_blk + 15) / 16 * 16;
+  int nat_cib = ((c16 + nat_blk - 1) / nat_blk + 15) / 16 * 16;
+  // Multi-block layers: ci blocks of at most 32 channels.  With the row loader (conv_tc3.cuh) a block costs ~1 us to
+  // convert whatever its width, and 32-channel blocks leave room for a double-buffered A ring and staging next to the
+  // weight ring (measured at config 2: 48 -> 32 channels took the forward from 1.340 to 1.271 ms; 16 gave 1.331 ms).
+  if (C_in > 64 && nat_cib > 32) nat_cib = 32;
   for (int cib = nat_cib; cib >= 16 && !best_cib; cib -= 16) {
     for (int resident = 1; resident >= 0 && !best_cib; --resident) {
       a.CIB = cib;
@@ -62,13 +66,6 @@ static bool tc2_plan(int C_in, int C_out, int K, ConvW* cw) {
   t->n_blk = (c16 + best_cib - 1) / best_cib;
   cw->tc2_resident = best_res;
   return true;
-}
-
-static void pack_tc(cudaStream_t s, const ConvW& cw, const TcW& t) {
-  const size_t total = t.elems() / 2;
-  const int blocks = (int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024);
-  pack_tc_weights_kernel<<<blocks, 256, 0, s>>>(cw.w, cw.C_in, cw.C_out, cw.K, t.CIB, t.n_blk, t.N_tile, t.n_ntiles,
-                                                (__nv_bfloat16*)t.w);
 }
 
 int tc_setup_kernels() {
@@ -237,11 +234,12 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   const bool small = false;
   // transform variant: 3 / 4 = lean path (direct rows, one ci block, a warp's <= 4 / <= 6 tasks of an item in one chunk)
   int mode = p[0].gen_w ? 1 : (p[0].up > 1 ? 2 : 0);
-  if (mode == 0 && p[0].down == 1 && p[0].n_blk == 1 && !getenv("FSVC_NO_LEAN")) {
+  if (mode == 0 && p[0].down == 1 && !getenv("FSVC_NO_LEAN")) {
     const int ntask = (p[0].CIB / 8) * ((kTc2M + 2 * (K / 2) * p[0].dil + 31) / 32);
     const int rounds = (ntask + 5) / 6;
-    if (rounds <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4)) mode = 3;
-    else if (rounds <= 6 && tc3_plan_smem(p[0], K, &cfg, false, 6) && cfg.a_slots >= 2) mode = 4;
+    const bool bulk = (K / 2) * p[0].dil <= 32;  // the window spans at most 6 aligned 32-row blocks
+    if (bulk && rounds <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4, true)) mode = 3;
+    else if (bulk && rounds <= 6 && tc3_plan_smem(p[0], K, &cfg, false, 6, true) && cfg.a_slots >= 2) mode = 4;
   }
   if (mode == 2 && p[0].down == 1 && p[0].up <= 8 && p[0].n_blk == 1 && !getenv("FSVC_NO_LEAN")) {
     const int Wd = kTc2M + 2 * (K / 2) * p[0].dil;
@@ -287,6 +285,10 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     flops += 2.0 * a.C_in * a.C_out * K * BT;
     elems += a.gen_w ? BT : (double)c.B * a.C_in * ((double)a.T_out / a.up);
     elems += BT * a.C_out * ((a.out ? 1 : 0) + (a.raw ? 1 : 0) + (a.res ? 1 : 0) + (a.gamma ? 2 : 0));
+    if (a.last_w) {  // folded conv_last
+      flops += 2.0 * BT * a.C_out * a.last_co;
+      elems += BT * a.last_co + (double)a.C_out * a.last_co;
+    }
     elems += (double)a.C_in * a.C_out * K;
   }
   c.launched(name, flops, 4.0 * elems);
@@ -308,6 +310,25 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
   const int T = frames * h->hop;
   const int S = h->cfg.spk_emb_size;
 
+  // conv_last folds into the last stage's final conv when that conv runs as one N tile / one sub-tile of two column
+  // halves (any last-stage width that is a multiple of 8 up to 32): exactly two atomic adds per output sample
+  const int C_last = h->cfg.mid_channels[n - 1];
+  const bool fold_last = C_last <= 32 && h->stage[n - 1].d27.tc2.n_ntiles == 1 && !getenv("FSVC_NO_FOLD_LAST");
+  // Small launches nothing on the conditioning chain depends on (speaker projections, PPG transpose, clears) run on a
+  // forked stream and rejoin before stage 0; a profiling run keeps them on the caller's stream (per-launch events).
+  cudaStream_t side = prof ? stream : h->side_stream;
+  if (!prof) {
+    cudaEventRecord(h->ev_side_fork, stream);
+    cudaStreamWaitEvent(side, h->ev_side_fork, 0);
+  }
+  if (fold_last) cudaMemsetAsync(out, 0, (size_t)B * h->cfg.out_channels * T * sizeof(float), side);
+  {  // the caller's (B, C, T') PPG tensor -> channels-last
+    if (h->ppg_ready) cudaStreamWaitEvent(side, h->ppg_ready, 0);  // fsvc_forward_host: upload on the copy stream
+    const int Cin = h->cfg.in_channels;
+    nct_to_ntc_kernel<<<dim3((frames + 31) / 32, (Cin + 31) / 32, B), 256, 0, side>>>(ppg, Cin, frames, ws.xin);
+    c.label = "";
+    c.launched("ppg_to_ntc", 0.0, 8.0 * B * Cin * frames);
+  }
   if (spk) {  // every stage's emb_projector(normalize(spk)) in one launch                fastsvc.py:135-137
     SpkProjArgs sp;
     memset(&sp, 0, sizeof(sp));
@@ -319,10 +340,11 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
     }
     int c_max = 0;
     for (int i = 0; i < n; ++i) c_max = sp.C[i] > c_max ? sp.C[i] : c_max;
-    spk_project_all_kernel<<<dim3(B, n, (c_max + 31) / 32), 256, 0, stream>>>(spk, S, sp);
+    spk_project_all_kernel<<<dim3(B, n, (c_max + 31) / 32), 256, 0, side>>>(spk, S, sp);
     c.label = "";
     c.launched("spk_project", 0.0, 0.0);
   }
+  if (!prof) cudaEventRecord(h->ev_side_join, side);
 
   // ---- conditioning chains, both branches per launch (fastsvc.py:180-193, 220-232) ----
   int T_prev = T, T_l = T;
@@ -439,13 +461,7 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
   }
 
   // ---- upsampling stages (fastsvc.py:80-140) ----
-  {  // the caller's (B, C, T') PPG tensor -> channels-last
-    if (h->ppg_ready) cudaStreamWaitEvent(stream, h->ppg_ready, 0);  // fsvc_forward_host: upload on the side stream
-    const int Cin = h->cfg.in_channels;
-    nct_to_ntc_kernel<<<dim3((frames + 31) / 32, (Cin + 31) / 32, B), 256, 0, stream>>>(ppg, Cin, frames, ws.xin);
-    c.label = "";
-    c.launched("ppg_to_ntc", 0.0, 8.0 * B * Cin * frames);
-  }
+  if (!prof) cudaStreamWaitEvent(stream, h->ev_side_join, 0);
   const float* x = ws.xin;
   int x_ld = h->cfg.in_channels, T_in = frames;
   for (int i = 0; i < n; ++i) {
@@ -526,13 +542,20 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
     pre(p[0]);
     p[0].res = ws.x_[i];
     p[0].res_ld = C;
-    launch_tc2(c, h, 3, p, 1, "d27_skip");
+    if (i == n - 1 && fold_last) {  // waveform = conv_last(out): written by this conv's epilogue      fastsvc.py:330
+      p[0].out = nullptr;
+      p[0].last_w = h->last.w;
+      p[0].last_b = h->last.b;
+      p[0].last_out = out;
+      p[0].last_co = h->cfg.out_channels;
+    }
+    launch_tc2(c, h, 3, p, 1, i == n - 1 && fold_last ? "d27_skip+last" : "d27_skip");
     x = ws.xs[i];
     x_ld = C;
     T_in = T_s;
   }
   // conv_last (1x1)                                                         fastsvc.py:330
-  {
+  if (!fold_last) {
     const long long BT = (long long)B * T;
     const int C = h->cfg.mid_channels[n - 1];
     conv_last_ntc_kernel<<<(unsigned)((BT + 255) / 256), 256, 0, stream>>>(x, C, T, BT, h->last.w, h->last.b,
@@ -600,15 +623,76 @@ void tc_fix_pointers(fsvc_handle* h) {
   }
 }
 
-void tc_pack_weights(fsvc_handle* h, cudaStream_t s) {
-  for (ConvW* cw : h->convs) {
-    if (cw->tc2.w) pack_tc(s, *cw, cw->tc2);
-    if (cw->nc_G) {
-      const size_t total = (size_t)cw->K * cw->nc_G * cw->nc_N * 8;
-      pack_tc_nc_weights_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-          cw->w, cw->C_in, cw->C_out, cw->K, cw->nc_G, cw->nc_N, (__nv_bfloat16*)cw->wnc);
+// Tensor-core weight packs as one launch over a device job table (kinds 4 / 5 of WJob): fp32 packed [C_in][K][C_out] ->
+// bf16 hi|lo in the tiled UMMA layouts of conv_tc3 (pack_tc_weights_kernel's format) and of the fused level kernel.
+static __global__ void __launch_bounds__(256) weight_jobs_tc_kernel(const WJob* __restrict__ jobs) {
+  const WJob j = jobs[blockIdx.y];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j.dst);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    if (j.kind == 4) {
+      const long long half = (long long)j.K * j.CIB * j.N_tile;
+      const int e = r % 8; r /= 8;
+      const int n = r % j.N_tile; r /= j.N_tile;
+      const int g = r % (j.CIB / 8); r /= (j.CIB / 8);
+      const int k = r % j.K; r /= j.K;
+      const int blk = r % j.n_blk; r /= j.n_blk;
+      const int nt = (int)r;
+      const int ci = blk * j.CIB + g * 8 + e, co = nt * j.N_tile + n;
+      float v = 0.f;
+      if (ci < j.C_in && co < j.C_out) v = j.w[((long long)ci * j.K + k) * j.C_out + co];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      const long long base = ((long long)(nt * j.n_blk + blk) * 2) * half + (((long long)k * (j.CIB / 8) + g) * j.N_tile + n) * 8 + e;
+      dst[base] = hi;
+      dst[base + half] = lo;
+    } else {
+      const int e = r % 8; r /= 8;
+      const int n = r % j.N; r /= j.N;
+      const int g = r % j.G; r /= j.G;
+      const int k = (int)r;
+      const int ci = g * 8 + e;
+      float v = 0.f;
+      if (ci < j.C_in && n < j.C_out) v = j.w[((long long)ci * j.K + k) * j.C_out + n];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      const long long base = (((long long)k * j.G + g) * 2 * j.N + n) * 8 + e;
+      dst[base] = hi;
+      dst[base + (long long)j.N * 8] = lo;
     }
   }
+}
+
+int tc_build_jobs(fsvc_handle* h) {
+  std::vector<WJob> jobs;
+  for (ConvW* cw : h->convs) {
+    if (cw->tc2.w) {
+      const TcW& t = cw->tc2;
+      WJob j;
+      memset(&j, 0, sizeof(j));
+      j.kind = 4; j.C_out = cw->C_out; j.C_in = cw->C_in; j.K = cw->K; j.w = cw->w; j.dst = (void*)t.w;
+      j.CIB = t.CIB; j.n_blk = t.n_blk; j.N_tile = t.N_tile; j.n_ntiles = t.n_ntiles;
+      j.total = (long long)(t.elems() / 2);
+      jobs.push_back(j);
+    }
+    if (cw->nc_G) {
+      WJob j;
+      memset(&j, 0, sizeof(j));
+      j.kind = 5; j.C_out = cw->C_out; j.C_in = cw->C_in; j.K = cw->K; j.w = cw->w; j.dst = (void*)cw->wnc;
+      j.G = cw->nc_G; j.N = cw->nc_N;
+      j.total = (long long)cw->K * cw->nc_G * cw->nc_N * 8;
+      jobs.push_back(j);
+    }
+  }
+  h->n_jobs_tc = (int)jobs.size();
+  if (jobs.empty()) return FSVC_OK;
+  FSVC_CUDA(cudaMalloc((void**)&h->jobs_tc, jobs.size() * sizeof(WJob)));
+  FSVC_CUDA(cudaMemcpy(h->jobs_tc, jobs.data(), jobs.size() * sizeof(WJob), cudaMemcpyHostToDevice));
+  return FSVC_OK;
+}
+
+void tc_pack_weights(fsvc_handle* h, cudaStream_t s) {
+  if (h->n_jobs_tc) weight_jobs_tc_kernel<<<dim3(16, h->n_jobs_tc), 256, 0, s>>>(h->jobs_tc);
 }
 
 size_t tc_workspace_bytes(const fsvc_handle* h, int B, int frames) {
@@ -617,3 +701,11 @@ size_t tc_workspace_bytes(const fsvc_handle* h, int B, int frames) {
 }
 
 }  // namespace fsvc
+
+#ifdef FSVC_TIMELINE
+// debug builds only (tools/timeline.py): copy the event stamps of the last forward
+extern "C" int fsvc_debug_timeline(unsigned long long* out, int n) {
+  FSVC_CUDA(cudaMemcpyFromSymbol(out, fsvc::g_tl, sizeof(unsigned long long) * (size_t)(n < 64 * 8 * 64 ? n : 64 * 8 * 64)));
+  return FSVC_OK;
+}
+#endif

@@ -98,28 +98,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// fp32 packed [C_in][K][C_out]  ->  TcW layout (hi/lo bf16, zero padded).
-__global__ void pack_tc_weights_kernel(const float* __restrict__ src, int C_in, int C_out, int K, int CIB, int n_blk,
-                                       int N_tile, int n_ntiles, __nv_bfloat16* __restrict__ dst) {
-  const size_t half = (size_t)K * CIB * N_tile;  // one (n_tile, blk, split) chunk
-  const size_t total = (size_t)n_ntiles * n_blk * half;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    size_t r = i;
-    const int e = r % 8; r /= 8;
-    const int n = r % N_tile; r /= N_tile;
-    const int g = r % (CIB / 8); r /= (CIB / 8);
-    const int k = r % K; r /= K;
-    const int blk = r % n_blk; r /= n_blk;
-    const int nt = (int)r;
-    const int ci = blk * CIB + g * 8 + e, co = nt * N_tile + n;
-    float v = 0.f;
-    if (ci < C_in && co < C_out) v = src[((size_t)ci * K + k) * C_out + co];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    const size_t base = ((size_t)(nt * n_blk + blk) * 2) * half + (((size_t)k * (CIB / 8) + g) * N_tile + n) * 8 + e;
-    dst[base] = hi;
-    dst[base + half] = lo;
-  }
-}
+// Packed tensor-core weights of one conv (TcW, fsvc_internal.h): fp32 packed [C_in][K][C_out] ->
+// [n_tile][ci_blk][hi|lo][tap][CIB/8][N_tile][8] bf16, zero padded; written by weight_jobs_tc_kernel (tc_forward.cu).
 
 }  // namespace fsvc

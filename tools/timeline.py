@@ -47,4 +47,9 @@ for slot, lab in enumerate(labels[:64]):
     ab = " ".join(f"{us(4 + i):5.1f}" for i in range(12) if t[4 + i])
     mb = " ".join(f"{us(20 + i):5.1f}" for i in range(12) if t[20 + i])
     print(f"{lab:22s} {recs[slot]['ms']*1e3:6.1f} | {us(1):5.1f} {us(2):5.1f} {us(3):5.1f} | {ab} | {mb} | {us(36):5.1f} {us(38):5.1f} {us(39):5.1f} {us(40):5.1f}")
+    if t[41] and t[47]:   # steady state, item 5: inside one iteration of each role (us since kernel entry)
+        print(f"    item 5  transform: top {us(41):.2f} staged {us(42):.2f} slot-free {us(43):.2f} converted {us(44):.2f} "
+              f"arrived {us(9):.2f} barrier {us(46):.2f} issued {us(47):.2f}")
+        print(f"            mma: wait-A {us(51):.2f} got-A {us(52):.2f} committed {us(53):.2f}   "
+              f"epilogue: wait-acc {us(48):.2f} got-acc {us(49):.2f} stored {us(50):.2f}")
     tl[slot] = 0
