@@ -345,7 +345,7 @@ def run_infer(args):
         clocks = sampler.stop() if rank == 0 else None
 
         parity = roof = cpu_base = omp1 = b1 = eager = None
-        if rank == 0:
+        if rank == 0 and not args.quick:
             # parity of what was just timed (2 utterances vs the CPU oracle port)
             tp = {k: torch.from_numpy(v) for k, v in params.items()}
             y = g(*devin)[:2].cpu()
@@ -707,6 +707,7 @@ def main():
     ap.add_argument("--config", default="infer", choices=["infer", "train", "convert"])
     ap.add_argument("--precision", default=os.environ.get("FSVC_MODE", "auto"))
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager-CUDA comparison leg")
+    ap.add_argument("--quick", action="store_true", help="infer: timing only (no parity / roofline / CPU legs); for A/B runs")
     ap.add_argument("--utts", type=int, default=10000, help="convert: utterances in the whole job")
     ap.add_argument("--batch", type=int, default=32, help="convert: utterances per launch")
     ap.add_argument("--ref-utts", type=int, default=100, help="convert: utterances of the CPU reference leg (0 = skip)")

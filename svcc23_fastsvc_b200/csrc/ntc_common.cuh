@@ -135,65 +135,68 @@ __device__ __forceinline__ void split_store(uint8_t* dst, uint32_t plane, const 
 
 // ---- small companions -------------------------------------------------------------------
 
-// Merge the per-32-step (mean, M2) partials [B][n_seg][C] of one (b, c) (Chan et al., double, fixed order)
-// and emit the affine the next conv applies on load: a = rstd, c = e - mean*rstd.
-// InstanceNorm2d: biased variance over the whole time axis, eps inside the sqrt (fastsvc.py:76,138).
-// One warp per (b, c): lane l merges segments l, l+32, ... (loads issued 8 at a time), then a 5-step
-// butterfly merges the lanes.  grid = ceil(B*C / 8) blocks of 256 threads.
+// Merge the per-32-step (mean, M2) partials [B][n_seg][C] of one (b, c) and emit the affine the next conv applies
+// on load: a = rstd, c = e - mean*rstd.  InstanceNorm2d: biased variance over the whole time axis, eps inside the sqrt
+// (fastsvc.py:76,138).  One warp per (b, c): lane l takes segments l, l+32, ... and accumulates, in double and in a
+// fixed order, the moments of the segment means about the FIRST segment's mean (n, sum n*d, sum n*d^2, sum M2) -- no
+// division in the loop (FP64 division is what made the Chan-style merge slow) -- then the lanes are added by a
+// butterfly whose two operands are always taken in lane order: bitwise deterministic.
+// grid = ceil(B*C / 8) blocks of 256 threads.
 __device__ __forceinline__ double shfl_xor_d(double v, int o) {
   int lo = __double2loint(v), hi = __double2hiint(v);
   lo = __shfl_xor_sync(0xffffffffu, lo, o);
   hi = __shfl_xor_sync(0xffffffffu, hi, o);
   return __hiloint2double(hi, lo);
 }
-__global__ void __launch_bounds__(256) in_finalize2_kernel(const float2* __restrict__ stats, int n_seg, int T, int C,
-                                                           int BC, const float* __restrict__ e, float eps,
-                                                           float* __restrict__ out_a, float* __restrict__ out_c) {
+struct InFinalizeArgs {
+  const float2* stats;
+  int n_seg, T, C, BC;
+  const float* e;
+  float eps;
+  float* out_a;
+  float* out_c;
+};
+__global__ void __launch_bounds__(256) in_finalize2_kernel(const InFinalizeArgs p) {
   const int lane = threadIdx.x & 31;
   const int bc = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (bc >= BC) return;
-  const int b = bc / C, c = bc - b * C;
-  const float2* sp = stats + (long long)b * n_seg * C + c;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  for (int s0 = lane; s0 < n_seg; s0 += 8 * 32) {
+  if (bc >= p.BC) return;
+  const int b = bc / p.C, c = bc - b * p.C;
+  const float2* sp = p.stats + (long long)b * p.n_seg * p.C + c;
+  const double piv = (double)__ldcg(sp).x;
+  double sw = 0.0, s1 = 0.0, s2 = 0.0, qq = 0.0;
+  for (int s0 = lane; s0 < p.n_seg; s0 += 8 * 32) {
     float2 pv[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int sg = s0 + 32 * u;
-      pv[u] = sg < n_seg ? __ldg(sp + (long long)sg * C) : make_float2(0.f, 0.f);
+      pv[u] = sg < p.n_seg ? __ldcg(sp + (long long)sg * p.C) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int sg = s0 + 32 * u;
-      if (sg < n_seg) {
-        const double nb = (double)min(32, T - sg * 32);
-        const double d = (double)pv[u].x - mean, nn = n + nb;
-        mean += d * nb / nn;
-        m2 += (double)pv[u].y + d * d * n * nb / nn;
-        n = nn;
-      }
+      const double nb = sg < p.n_seg ? (double)min(32, p.T - sg * 32) : 0.0;
+      const double d = (double)pv[u].x - piv;
+      sw += nb;
+      s1 = fma(nb, d, s1);
+      s2 = fma(nb * d, d, s2);
+      qq += (double)pv[u].y;
     }
   }
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const double n2 = shfl_xor_d(n, o), mean2 = shfl_xor_d(mean, o), m22 = shfl_xor_d(m2, o);
-    // merge (lower lane's partial, upper lane's partial) in that order on both lanes: bitwise symmetric
-    const bool low = (lane & o) == 0;
-    const double na = low ? n : n2, ma = low ? mean : mean2, qa = low ? m2 : m22;
-    const double nb = low ? n2 : n, mb = low ? mean2 : mean, qb = low ? m22 : m2;
-    const double nn = na + nb;
-    if (nn > 0.0) {
-      const double d = mb - ma;
-      mean = ma + d * nb / nn;
-      m2 = qa + qb + d * d * na * nb / nn;
-    }
-    n = nn;
+    const double w2 = shfl_xor_d(sw, o), a2 = shfl_xor_d(s1, o), b2 = shfl_xor_d(s2, o), q2 = shfl_xor_d(qq, o);
+    const bool low = (lane & o) == 0;  // (lower lane) + (upper lane) on both lanes: the same bits everywhere
+    sw = low ? sw + w2 : w2 + sw;
+    s1 = low ? s1 + a2 : a2 + s1;
+    s2 = low ? s2 + b2 : b2 + s2;
+    qq = low ? qq + q2 : q2 + qq;
   }
   if (lane == 0) {
-    const double var = m2 / (double)T;
-    const double rstd = 1.0 / sqrt(var + (double)eps);
-    out_a[bc] = (float)rstd;
-    out_c[bc] = (float)((double)(e ? e[bc] : 0.f) - mean * rstd);
+    const double dm = s1 / sw;
+    const double var = fmax(qq + s2 - s1 * dm, 0.0) / sw;
+    const double rstd = 1.0 / sqrt(var + (double)p.eps);
+    p.out_a[bc] = (float)rstd;
+    p.out_c[bc] = (float)((double)(p.e ? p.e[bc] : 0.f) - (piv + dm) * rstd);
   }
 }
 
