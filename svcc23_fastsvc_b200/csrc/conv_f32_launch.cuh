@@ -18,7 +18,10 @@ static inline void launch_conv_t(const ConvArgs& a, int B, cudaStream_t s) {
   conv1d_f32_kernel<RC, RT, K><<<grid, kConvThreads, smem, s>>>(a);
 }
 
-static inline int conv_rt(int T_out) { return T_out >= 1024 ? 8 : 4; }
+// Time steps per lane.  Long layers take 8 (256-step tiles); short ones shrink the tile until the launch has a few
+// CTAs per SM -- at T <= 816 (the low-rate levels / stages of a training batch) 128-step tiles left 64 CTAs on 148
+// SMs, one per SM, each running its 12 input-channel tiles back to back with nothing to hide the loads behind.
+static inline int conv_rt(int T_out) { return T_out >= 1024 ? 8 : (T_out > 512 ? 4 : (T_out > 192 ? 2 : 1)); }
 static inline int conv_tile_len(int T_out) { return 32 * conv_rt(T_out); }
 
 static inline int conv_rc(int C_out) {
@@ -38,8 +41,9 @@ static inline void launch_conv(Ctx& c, const ConvArgs& a, int K, const char* nam
     if (K == 3) launch_conv_t<RC_, RT_, 3>(a, c.B, c.stream);                \
     else launch_conv_t<RC_, RT_, 1>(a, c.B, c.stream);                       \
   }
-  FSVC_CASE(1, 4) FSVC_CASE(1, 8) FSVC_CASE(2, 4) FSVC_CASE(2, 8) FSVC_CASE(3, 4) FSVC_CASE(3, 8)
-  FSVC_CASE(4, 4) FSVC_CASE(4, 8) FSVC_CASE(6, 4) FSVC_CASE(6, 8)
+  FSVC_CASE(1, 1) FSVC_CASE(1, 2) FSVC_CASE(1, 4) FSVC_CASE(1, 8) FSVC_CASE(2, 1) FSVC_CASE(2, 2) FSVC_CASE(2, 4)
+  FSVC_CASE(2, 8) FSVC_CASE(3, 1) FSVC_CASE(3, 2) FSVC_CASE(3, 4) FSVC_CASE(3, 8) FSVC_CASE(4, 1) FSVC_CASE(4, 2)
+  FSVC_CASE(4, 4) FSVC_CASE(4, 8) FSVC_CASE(6, 1) FSVC_CASE(6, 2) FSVC_CASE(6, 4) FSVC_CASE(6, 8)
 #undef FSVC_CASE
   // algorithmic work of this launch: 2*Cin*Cout*K*T flops; every operand tensor touched once
   const double BT = (double)c.B * a.T_out;
