@@ -47,6 +47,7 @@ constexpr int kTc3ChunkItems = 4;      // 16-byte-chunk items per transform thre
 struct Tc3Cfg {
   int n_prob;  // 1 or 2 problems (blockIdx.x % n_prob); problem 1 = problem 0 + the pointer deltas below
   int B, m_tiles;
+  int b_lo, b_hi;  // utterances [b_lo, b_hi) of the batch are processed by this launch (normally 0, B)
   int nsub;       // epilogue sub-tile width (channels, multiple of 8, <= 32)
   int a_slots;    // depth of the A ring (1..3)
   int scr_pitch;  // floats per row of the per-warp statistics scratch (12 or 20)
@@ -307,9 +308,9 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   // in L2 and the utterance (hence the InstanceNorm affine in shared memory) changes at most a few times per CTA
   const int n_cta = gridDim.x / (c.n_prob * a.n_ntiles);
   const int cta = rest / a.n_ntiles;
-  const int n_all = c.B * c.m_tiles;
-  const int first = (int)((long long)cta * n_all / n_cta);
-  const int n_m = (int)((long long)(cta + 1) * n_all / n_cta);
+  const int n_all = (c.b_hi - c.b_lo) * c.m_tiles, item_lo = c.b_lo * c.m_tiles;
+  const int first = item_lo + (int)((long long)cta * n_all / n_cta);
+  const int n_m = item_lo + (int)((long long)(cta + 1) * n_all / n_cta);
   constexpr int step = 1;
 
   const int halo = (K / 2) * a.dil;

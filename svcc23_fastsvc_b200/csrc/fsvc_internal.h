@@ -112,6 +112,16 @@ struct fsvc_handle {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_ppg = nullptr;
   cudaEvent_t ppg_ready = nullptr;  // set for the duration of one fsvc_forward_host call
+  // fsvc_forward_host: the two signals are uploaded in two batch halves; the fused level-0 kernel is launched per half
+  // so the first half computes while the second is still on the wire.  sig_ready[k] / sig_split are set for the call.
+  cudaEvent_t ev_sig[2] = {nullptr, nullptr};
+  cudaEvent_t sig_ready[2] = {nullptr, nullptr};
+  int sig_split = 0;  // utterances in the first half
+  // fsvc_forward_host: host destination of the waveform (set for the call); the tensor-core forward copies the first
+  // half back itself, while the last conv of the second half runs, and reports how many floats it has taken care of
+  float* out_host = nullptr;
+  size_t out_host_done = 0;
+  cudaEvent_t ev_out_half = nullptr, ev_out_done = nullptr;
   // tensor-core forward: small independent launches (speaker projections, PPG transpose) run on a forked stream
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;

@@ -59,7 +59,8 @@ struct LevelFusedArgs {
   const float* b_out;        // [2C]
   float* y_dec[2];           // [B][T/dec][C] or nullptr
   float* gb;                 // [B][T][2C]
-  int C, T, B, dec;
+  int C, T, B, dec;          // B: utterances of THIS launch, starting at utterance b_off
+  int b_off;
   int n_tiles;               // ceil(T / kLfValid)
   int Gp;                    // groups of a C->C conv incl. K padding (even)
   int N1;                    // N of the C->C convs (multiple of 16, <= 32)
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
   const uint32_t buf_off0 = L.off_buf[0], buf_bytes = L.buf_bytes;
   // buffers: X_br = buffer 2*br (a1, then y), Y_br = buffer 2*br+1 (a2, then h)
 
+  if (tid == 0) FSVC_TL(63, 0);
   griddep_launch_dependents();
   if (tid == 0) {
     mbar_init(bar_ready, kLfWorkers);
@@ -252,10 +254,12 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           accum = 1u;
         }
       };
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int tl_it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl_it) {
         uint32_t di = 0u;
         for (int layer = 0; layer < 3; ++layer) {      // a1 (X) -> a2 (Y) -> y (X) -> h (Y), branches interleaved
           for (int br = 0; br < 2; ++br) {
+            if (leader && tl_it == 3) FSVC_TL(63, 1 + (layer * 2 + br) * 3);
             if (br == 0) {
               mbar_wait2(bar_ready, ready_phase0);
               ready_phase0 ^= 1u;
@@ -264,22 +268,27 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
               ready_phase1 ^= 1u;
             }
             tc_fence_after();
+            if (leader && tl_it == 3) FSVC_TL(63, 2 + (layer * 2 + br) * 3);
             for (int mt = 0; mt < 2; ++mt) {
               issue_mtile(tmem_u + (uint32_t)(2 * br + mt) * 64u, di, n1, idesc_c, idesc_h);
               if (leader) umma_commit(bar_acc + 2 * br + mt);
             }
+            if (leader && tl_it == 3) FSVC_TL(63, 3 + (layer * 2 + br) * 3);
           }
         }
         // merged film_out over the virtual channel concat [h_lft (Y_0) | h_sine (Y_1)]
+        if (leader && tl_it == 3) FSVC_TL(63, 19);
         mbar_wait2(bar_ready, ready_phase0);
         ready_phase0 ^= 1u;
         mbar_wait2(bar_ready + 1, ready_phase1);
         ready_phase1 ^= 1u;
         tc_fence_after();
+        if (leader && tl_it == 3) FSVC_TL(63, 20);
         for (int mt = 0; mt < 2; ++mt) {
           issue_mtile(tmem_u + (uint32_t)mt * 128u, di, n2, idesc_oc, idesc_oh);
           if (leader) umma_commit(bar_acc + mt);
         }
+        if (leader && tl_it == 3) FSVC_TL(63, 21);
       }
       __syncwarp();
     }
@@ -289,8 +298,10 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     griddep_wait();  // the outputs of this kernel may still be read by the previous forward's kernels
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int b = item / p.n_tiles, t0 = (item - b * p.n_tiles) * kLfValid;
+    int tl_it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl_it) {
+      const int bl = item / p.n_tiles, b = p.b_off + bl, t0 = (item - bl * p.n_tiles) * kLfValid;
+      if (tid == 0 && tl_it == 3) FSVC_TL(63, 24);
       // ---- raw signal windows of both branches ----
       for (int i = tid; i < 2 * kLfRows; i += kLfWorkers) {
         const int br = i >= kLfRows, j = i - br * kLfRows;
@@ -298,6 +309,7 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         s_sig[i] = (t >= 0 && t < p.T) ? __ldg(p.sig[br] + (long long)b * p.T + t) : 0.f;
       }
       named_bar_sync(1, kLfWorkers);
+      if (tid == 0 && tl_it == 3) FSVC_TL(63, 25);
       // ---- a1 = Conv3_d1(lrelu(x)) on the CUDA cores, stored as lrelu(a1): rows time t0-8 .. t0+247 ----
       for (int br = 0; br < 2; ++br) {
         const float* sg = s_sig + br * kLfRows;
@@ -326,6 +338,7 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         }
         fence_proxy_async();
         mbar_arrive(bar_ready + br);
+        if (tid == 0 && tl_it == 3) FSVC_TL(63, 26 + br);
       }
       // ---- three tensor-core layers per branch, branches interleaved:
       //      TMEM -> (hi + lo halves, bias, residual, activation, zero padding) -> bf16 hi|lo -> smem ----
@@ -337,8 +350,10 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           uint8_t* dst = smem + buf_off0 + (uint32_t)(2 * br + (layer == 1 ? 0 : 1)) * buf_bytes;
           const float* bias = par + (layer == 0 ? kLfBC2 : (layer == 1 ? kLfBC4 : kLfBFilm)) * 32;
           const uint32_t ph = br == 0 ? acc_phase0 : acc_phase1;
+          if (tid == 0 && tl_it == 3) FSVC_TL(63, 28 + (layer * 2 + br) * 3);
           for (int mt = 0; mt < 2; ++mt) {
             mbar_wait2(bar_acc + 2 * br + mt, ph);
+            if (tid == 0 && tl_it == 3 && mt == 0) FSVC_TL(63, 29 + (layer * 2 + br) * 3);
             tc_fence_after();
             const int tau = s + 128 * mt + q * 32 + lane, t = t0 + tau;
             const bool in_seq = t >= 0 && t < p.T;
@@ -375,8 +390,10 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           fence_proxy_async();
           tc_fence_before();
           mbar_arrive(bar_ready + br);
+          if (tid == 0 && tl_it == 3) FSVC_TL(63, 30 + (layer * 2 + br) * 3);
         }
       }
+      if (tid == 0 && tl_it == 3) FSVC_TL(63, 46);
       // ---- merged film_out: gamma | beta rows straight to HBM ----
       for (int mt = 0; mt < 2; ++mt) {
         mbar_wait2(bar_acc + mt, acc_phase0);
@@ -399,11 +416,13 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
       }
       acc_phase0 ^= 1u;
       tc_fence_before();
+      if (tid == 0 && tl_it == 3) FSVC_TL(63, 48);
       // (the next item's first MMAs are gated by bar_ready, which every worker arrives on only after this point)
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) FSVC_TL(63, 40);
   if (warp == 12) {
     __syncwarp();
     tmem_dealloc(tmem, 256);

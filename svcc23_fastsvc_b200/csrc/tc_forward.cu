@@ -194,7 +194,9 @@ static void launch_pdl(Kern kern, dim3 grid, int block, size_t smem, cudaStream_
 
 // Launch 1 or 2 problems of identical shape and flags (the two conditioning branches) as one persistent grid
 // of the warp-specialised kernel; problem 1 is expressed as pointer deltas against problem 0.
-static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, int n_prob, const char* name) {
+static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, int n_prob, const char* name, int b_lo = 0,
+                       int b_hi = -1) {
+  if (b_hi < 0) b_hi = c.B;
   Tc3Launch L;
   memset(&L, 0, sizeof(L));
   L.a = p[0];
@@ -225,9 +227,11 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   Tc3Cfg& cfg = L.c;
   cfg.n_prob = n_prob;
   cfg.B = c.B;
+  cfg.b_lo = b_lo;
+  cfg.b_hi = b_hi;
   cfg.m_tiles = (p[0].T_out + kTc2M - 1) / kTc2M;
   const int groups = n_prob * p[0].n_ntiles;
-  const int items = c.B * cfg.m_tiles;
+  const int items = (b_hi - b_lo) * cfg.m_tiles;
   // two half-size CTAs per SM when the conv allows it and there is enough work to keep both pipelines busy
   // (measured: two 224-thread CTAs per SM are no faster than one 512-thread CTA on any layer -- kept as a template
   //  option of the kernel, not instantiated)
@@ -281,9 +285,9 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   double flops = 0, elems = 0;
   for (int i = 0; i < n_prob; ++i) {
     const Tc2Args& a = p[i];
-    const double BT = (double)c.B * a.T_out;
+    const double BT = (double)(b_hi - b_lo) * a.T_out;
     flops += 2.0 * a.C_in * a.C_out * K * BT;
-    elems += a.gen_w ? BT : (double)c.B * a.C_in * ((double)a.T_out / a.up);
+    elems += a.gen_w ? BT : (double)(b_hi - b_lo) * a.C_in * ((double)a.T_out / a.up);
     elems += BT * a.C_out * ((a.out ? 1 : 0) + (a.raw ? 1 : 0) + (a.res ? 1 : 0) + (a.gamma ? 2 : 0));
     if (a.last_w) {  // folded conv_last
       flops += 2.0 * BT * a.C_out * a.last_co;
@@ -346,6 +350,8 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
   }
   if (!prof) cudaEventRecord(h->ev_side_join, side);
 
+  // fsvc_forward_host: without the fused level-0 kernel (which takes the signals half by half) wait for both halves here
+  if (!h->l0_fused && h->sig_ready[1]) cudaStreamWaitEvent(stream, h->sig_ready[1], 0);
   // ---- conditioning chains, both branches per launch (fastsvc.py:180-193, 220-232) ----
   int T_prev = T, T_l = T;
   bool fused_l0 = false;
@@ -380,17 +386,25 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
       fa.gb = ws.GB[0];
       fa.C = C;
       fa.T = T_l;
-      fa.B = B;
       fa.dec = dec;
       fa.n_tiles = (T_l + kLfValid - 1) / kLfValid;
       fa.Gp = lw.c2[0].nc_G;
       fa.N1 = lw.c2[0].nc_N;
       fa.N2 = lw.film_out.nc_N;
       fa.slope = c.slope;
-      const int items = B * fa.n_tiles;
-      const int grid = items < h->num_sms ? items : h->num_sms;
       if (level_fused_fill_desc(&fa) != 0) return fail(FSVC_E_INVALID, "internal: fused level descriptor table overflow");
-      launch_pdl(level0_fused_kernel, dim3(grid), kLfThreads, LF.total, stream, fa);
+      // fsvc_forward_host uploads the signals in two batch halves: one launch per half, each behind its own event
+      const int n_part = (h->sig_ready[0] && h->sig_split > 0 && h->sig_split < B) ? 2 : 1;
+      for (int part = 0; part < n_part; ++part) {
+        fa.b_off = part == 0 ? 0 : h->sig_split;
+        fa.B = n_part == 1 ? B : (part == 0 ? h->sig_split : B - h->sig_split);
+        if (h->sig_ready[part]) cudaStreamWaitEvent(stream, h->sig_ready[part], 0);
+        if (n_part == 1 && h->sig_ready[1]) cudaStreamWaitEvent(stream, h->sig_ready[1], 0);
+        const int items = fa.B * fa.n_tiles;
+        const int grid = items < h->num_sms ? items : h->num_sms;
+        launch_pdl(level0_fused_kernel, dim3(grid), kLfThreads, LF.total, stream, fa);
+        if (part > 0) c.launches++;
+      }
       const double BT = (double)B * T_l;
       // both branches: first conv (3) + 1x1 residual (1) + d2, d4, FiLM conv (9C) MACs per channel and step; merged
       // film_out: 2C -> 2C, k = 3 (12C per channel); SURVEY 8d: 17.9 GFLOP at B = 32, C = 24, T = 16000
@@ -560,7 +574,21 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
       p[0].last_out = out;
       p[0].last_co = h->cfg.out_channels;
     }
-    launch_tc2(c, h, 3, p, 1, i == n - 1 && fold_last ? "d27_skip+last" : "d27_skip");
+    if (i == n - 1 && fold_last && h->out_host && B > 1 && !prof) {
+      // fsvc_forward_host: the waveform of the first half of the batch travels back while the second half's last conv
+      // runs (items are ordered by utterance, so an item range is an utterance range)
+      const int B0 = (B + 1) / 2;
+      const size_t half = (size_t)B0 * h->cfg.out_channels * T;
+      launch_tc2(c, h, 3, p, 1, "d27_skip+last", 0, B0);
+      cudaEventRecord(h->ev_out_half, stream);
+      cudaStreamWaitEvent(h->copy_stream, h->ev_out_half, 0);
+      cudaMemcpyAsync(h->out_host, out, half * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream);
+      cudaEventRecord(h->ev_out_done, h->copy_stream);
+      launch_tc2(c, h, 3, p, 1, "d27_skip+last", B0, B);
+      h->out_host_done = half;
+    } else {
+      launch_tc2(c, h, 3, p, 1, i == n - 1 && fold_last ? "d27_skip+last" : "d27_skip");
+    }
     x = ws.xs[i];
     x_ld = C;
     T_in = T_s;

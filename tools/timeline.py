@@ -53,3 +53,16 @@ for slot, lab in enumerate(labels[:64]):
         print(f"            mma: wait-A {us(51):.2f} got-A {us(52):.2f} committed {us(53):.2f}   "
               f"epilogue: wait-acc {us(48):.2f} got-acc {us(49):.2f} stored {us(50):.2f}")
     tl[slot] = 0
+
+# fused level-0 kernel (slot 63): one steady-state item (the CTA's 4th), microseconds since that item's start
+t = tl[63, 0]
+if t[0] and t[24]:
+    rel = lambda e: (t[e] - t[24]) / 1e3 if t[e] else float("nan")
+    print(f"\nlevel0_fused_kernel: kernel {(t[40] - t[0]) / 1e3:.1f} us; item 3 of CTA 0, us since the item started "
+          f"(signals loaded {rel(25):.2f}, a1 stored br0 {rel(26):.2f} br1 {rel(27):.2f})")
+    for layer in range(3):
+        for br in range(2):
+            i = (layer * 2 + br) * 3
+            print(f"  layer {layer} br {br}: mma wait {rel(1 + i):.2f} -> go {rel(2 + i):.2f} -> issued {rel(3 + i):.2f} | "
+                  f"workers wait {rel(28 + i):.2f} -> acc {rel(29 + i):.2f} -> stored {rel(30 + i):.2f}")
+    print(f"  film_out   : mma wait {rel(19):.2f} -> go {rel(20):.2f} -> issued {rel(21):.2f} | workers from {rel(46):.2f} -> stored {rel(48):.2f}")
