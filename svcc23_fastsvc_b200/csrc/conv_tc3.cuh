@@ -60,6 +60,8 @@ struct Tc3Cfg {
 
 struct Tc3Launch {
   Tc2Args a;
+  Tc2Args b;   // hetero launches: problem 1's own argument block (same shapes and tiling, different prologue /
+  int hetero;  // epilogue flags and tensors), instead of pointer deltas against problem 0
   long long d_in, d_w, d_bias, d_gen_w, d_gen_b, d_res, d_gres_w, d_gres_b, d_gres_x, d_raw, d_out;  // elements
   Tc3Cfg c;
   int tl_slot;  // launch index inside the forward (event timeline builds only)
@@ -298,10 +300,10 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   constexpr int kTc3XformThreads = SH::kXT, kTc3EpiThreads = SH::kET;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw;
-  const Tc2Args& a = L.a;
   const Tc3Cfg& c = L.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int prob = blockIdx.x % c.n_prob;
+  const Tc2Args& a = (L.hetero && prob == 1) ? L.b : L.a;
   const int rest = blockIdx.x / c.n_prob;
   const int nt = rest % a.n_ntiles;
   // items (utterance, 128-step tile) of this CTA: one contiguous range -- neighbouring tiles share their halo rows

@@ -298,17 +298,32 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     griddep_wait();  // the outputs of this kernel may still be read by the previous forward's kernels
+    // raw signal windows of both branches (index i <-> branch i / kLfRows, time t0 - 10 + i % kLfRows): this thread's
+    // <= 2 samples of the NEXT item are requested an item ahead, so their latency is off the item's critical path
+    // (measured: 0.8 of an item's 11.4 us went to this load; 187 -> 174 us per launch.  Also computing the next item's
+    // first conv into registers under this item's second layer measured slower, 179 us: the extra barrier and work
+    // delay the epilogues the tensor core is waiting for)
+    float sig_pre[2];
+    auto prefetch_signals = [&](int item) {
+      const int bl = item / p.n_tiles, b = p.b_off + bl, t0 = (item - bl * p.n_tiles) * kLfValid;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * kLfWorkers;
+        const int br = i >= kLfRows, j = i - br * kLfRows;
+        const int t = t0 - 10 + j;
+        sig_pre[k] = (i < 2 * kLfRows && t >= 0 && t < p.T) ? __ldg(p.sig[br] + (long long)b * p.T + t) : 0.f;
+      }
+    };
+    if ((int)blockIdx.x < n_items) prefetch_signals(blockIdx.x);
     int tl_it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl_it) {
       const int bl = item / p.n_tiles, b = p.b_off + bl, t0 = (item - bl * p.n_tiles) * kLfValid;
       if (tid == 0 && tl_it == 3) FSVC_TL(63, 24);
-      // ---- raw signal windows of both branches ----
-      for (int i = tid; i < 2 * kLfRows; i += kLfWorkers) {
-        const int br = i >= kLfRows, j = i - br * kLfRows;
-        const int t = t0 - 10 + j;
-        s_sig[i] = (t >= 0 && t < p.T) ? __ldg(p.sig[br] + (long long)b * p.T + t) : 0.f;
-      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        if (tid + k * kLfWorkers < 2 * kLfRows) s_sig[tid + k * kLfWorkers] = sig_pre[k];
       named_bar_sync(1, kLfWorkers);
+      if (item + (int)gridDim.x < n_items) prefetch_signals(item + gridDim.x);
       if (tid == 0 && tl_it == 3) FSVC_TL(63, 25);
       // ---- a1 = Conv3_d1(lrelu(x)) on the CUDA cores, stored as lrelu(a1): rows time t0-8 .. t0+247 ----
       for (int br = 0; br < 2; ++br) {

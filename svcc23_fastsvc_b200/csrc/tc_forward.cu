@@ -194,13 +194,26 @@ static void launch_pdl(Kern kern, dim3 grid, int block, size_t smem, cudaStream_
 
 // Launch 1 or 2 problems of identical shape and flags (the two conditioning branches) as one persistent grid
 // of the warp-specialised kernel; problem 1 is expressed as pointer deltas against problem 0.
+// `hetero`: the two problems share shapes and tiling but not prologue / epilogue (a stage's residual conv and its
+// upsampling conv read the same h0): each gets its own argument block.
 static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, int n_prob, const char* name, int b_lo = 0,
-                       int b_hi = -1) {
+                       int b_hi = -1, bool hetero = false) {
   if (b_hi < 0) b_hi = c.B;
   Tc3Launch L;
   memset(&L, 0, sizeof(L));
   L.a = p[0];
-  if (n_prob == 2) {
+  if (n_prob == 2 && hetero) {
+    const Tc2Args &x = p[0], &y = p[1];
+    L.b = y;
+    L.hetero = 1;
+    if (x.up != y.up || x.down != y.down || x.dil != y.dil || x.C_in != y.C_in || x.C_out != y.C_out ||
+        x.T_out != y.T_out || x.T_in != y.T_in || x.in_ld != y.in_ld || x.CIB != y.CIB || x.n_blk != y.n_blk ||
+        x.N_tile != y.N_tile || x.n_ntiles != y.n_ntiles || x.w_resident != y.w_resident || x.gen_w || y.gen_w ||
+        x.pre_stats || y.pre_stats || x.pre_a || y.pre_a) {
+      c.err = 2;
+      return;
+    }
+  } else if (n_prob == 2) {
     const Tc2Args &x = p[0], &y = p[1];
     L.d_in = y.in - x.in;
     L.d_w = y.w - x.w;
@@ -536,15 +549,20 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
     p[0] = tc2_args(c, w.first, x, x_ld, T_in, T_in, 1, ws.h0[i], C);
     launch_tc2(c, h, 3, p, 1, "conv_first");
     // xr = Conv3(repeat_r(h0)) ; t1 = gamma*lrelu(Conv3(repeat_r(lrelu(h0)))) + beta   :94, :97-98
+    // (one launch: both read h0 and have the same shape; the CTAs are split between the two problems)
     p[0] = tc2_args(c, w.res, ws.h0[i], C, T_in, T_s, 1, ws.xr[i], C);
     p[0].up = r;
-    launch_tc2(c, h, 3, p, 1, "residual");
-    p[0] = tc2_args(c, w.up, ws.h0[i], C, T_in, T_s, 1, ws.t1[i], C);
-    p[0].up = r;
-    p[0].pre_lrelu = 1;
-    p[0].post_lrelu = 1;
-    film(p[0]);
-    launch_tc2(c, h, 3, p, 1, "up_film");
+    p[1] = tc2_args(c, w.up, ws.h0[i], C, T_in, T_s, 1, ws.t1[i], C);
+    p[1].up = r;
+    p[1].pre_lrelu = 1;
+    p[1].post_lrelu = 1;
+    film(p[1]);
+    if (w.res.tc2_resident == w.up.tc2_resident && !getenv("FSVC_NO_MERGE")) {
+      launch_tc2(c, h, 3, p, 2, "residual+up_film", 0, -1, true);
+    } else {
+      launch_tc2(c, h, 3, p, 1, "residual");
+      launch_tc2(c, h, 3, p + 1, 1, "up_film");
+    }
     finalize();
     // x_ = Conv3_d3(lrelu(IN(t1)+e)) + xr ; t2 = gamma*x_ + beta            :99-105
     p[0] = tc2_args(c, w.d3, ws.t1[i], C, T_s, T_s, 3, ws.t2[i], C);
