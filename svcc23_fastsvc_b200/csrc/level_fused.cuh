@@ -97,7 +97,7 @@ __host__ __device__ inline LevelFusedSmem level_fused_smem(int C, int Gp, int N1
   off = (off + 15u) & ~15u;
   s.off_desc = off; off += (6u * 2u * 3u * (Gp / 2) + 2u * 3u * (G2 / 2)) * 24u;  // precomputed UMMA descriptors
   off = (off + 15u) & ~15u;
-  s.off_bar = off; off += 8 * 8 + 16;
+  s.off_bar = off; off += 12 * 8 + 16;
   s.total = off;
   return s;
 }
@@ -111,28 +111,46 @@ __host__ inline int level_fused_fill_desc(LevelFusedArgs* p) {
   const int C = p->C, G = C >> 3, Gp = p->Gp;
   const LevelFusedSmem L = level_fused_smem(C, Gp, p->N1, p->N2);
   const uint32_t strip = kLfRows * 16u, plane = (uint32_t)G * strip, buf_bytes = L.buf_bytes;
-  const uint32_t n1 = 3u * (uint32_t)(Gp / 2), G2 = 2u * (uint32_t)G, n2 = 3u * (G2 / 2);
+  // K = 16 chunks of a C -> C conv: pairs of (tap, 8-channel group) columns.  A column pair need not be adjacent --
+  // the descriptor's leading-dimension offset is the distance between its two columns, for A and for B -- so the
+  // 3 taps x G groups are packed into ceil(3G / 2) chunks instead of 3 * ceil(G / 2) (C = 24: 5 instead of 6 MMA
+  // pairs per tap set; the tensor pipe is what bounds this kernel): inside a tap groups pair up (g, g+1); with G odd
+  // the last groups of taps 0 and 1 pair with each other and the last group of tap 2 with the shared zero strip.
+  // Every pair's second column lies at a higher address than its first, in the activation buffer and in the weights.
+  struct Col { int k, g; };   // g < 0: zero strip
+  Col pairs[16][2];
+  int np = 0;
+  for (int k = 0; k < 3; ++k)
+    for (int g = 0; g + 1 < G; g += 2) { pairs[np][0] = {k, g}; pairs[np][1] = {k, g + 1}; ++np; }
+  if (G & 1) {
+    pairs[np][0] = {0, G - 1}; pairs[np][1] = {1, G - 1}; ++np;
+    pairs[np][0] = {2, G - 1}; pairs[np][1] = {2, -1}; ++np;
+  }
+  const uint32_t n1 = (uint32_t)np, G2 = 2u * (uint32_t)G, n2 = 3u * (G2 / 2);
   const uint32_t n_chain = 6u * 2u * n1, n_all = n_chain + 2u * n2;
   if (n_all > (uint32_t)kLfMaxDesc) return -1;
   const uint32_t buf0 = L.off_buf[0], zero_addr = L.off_zero, w_base = 0;
+  uint32_t b_lbo = 0;
   for (uint32_t e = 0; e < n_all; ++e) {
     uint32_t a0, a1h, a1l, b_addr, b_grp;
     if (e < n_chain) {
       const uint32_t lb = e / (2u * n1), r = e - lb * 2u * n1;
       const int layer = (int)(lb >> 1), br = (int)(lb & 1u);
       const int mt = (int)(r / n1), kk = (int)(r - (uint32_t)mt * n1);
-      const int k = kk / (Gp / 2), kc = kk - k * (Gp / 2);
       const int s0 = layer == 0 ? -6 : (layer == 1 ? -2 : -1), d = layer == 0 ? 2 : (layer == 1 ? 4 : 1);
       const int src = layer == 1 ? 1 : 0;  // a1 / y live in X (0), a2 in Y (1)
       const uint32_t w_addr = w_base + (layer == 0 ? L.off_w_c2[br] : (layer == 1 ? L.off_w_c4[br] : L.off_w_film[br]));
-      const uint32_t rbytes = (uint32_t)(s0 + kLfHalo - d + k * d + 128 * mt) * 16u;
-      const int g0 = 2 * kc, g1 = g0 + 1;
-      a0 = buf0 + (uint32_t)(2 * br + src) * buf_bytes + (uint32_t)g0 * strip + rbytes;
-      // second 8-channel column: the next real group, or the shared zero strip for the K padding
-      a1h = g1 < G ? a0 + strip : zero_addr + rbytes;
-      a1l = g1 < G ? a0 + plane + strip : zero_addr + rbytes;
+      const Col c0 = pairs[kk][0], c1 = pairs[kk][1];
+      auto rbytes = [&](int k) { return (uint32_t)(s0 + kLfHalo - d + k * d + 128 * mt) * 16u; };
+      const uint32_t abase = buf0 + (uint32_t)(2 * br + src) * buf_bytes;
+      a0 = abase + (uint32_t)c0.g * strip + rbytes(c0.k);
+      // second 8-channel column: another (tap, group) of the same buffer, or the shared zero strip for the K padding
+      a1h = c1.g >= 0 ? abase + (uint32_t)c1.g * strip + rbytes(c1.k) : zero_addr + rbytes(c0.k);
+      a1l = c1.g >= 0 ? a1h + plane : a1h;
       b_grp = 2u * (uint32_t)p->N1 * 16u;
-      b_addr = w_addr + ((uint32_t)k * Gp + g0) * b_grp;
+      b_addr = w_addr + ((uint32_t)c0.k * Gp + c0.g) * b_grp;
+      // (against the zero strip any finite weights do: the next block of the packed layout, zero padding itself)
+      b_lbo = c1.g >= 0 ? w_addr + ((uint32_t)c1.k * Gp + c1.g) * b_grp - b_addr : b_grp;
     } else {
       const uint32_t r = e - n_chain;
       const int mt = (int)(r / n2), kk = (int)(r - (uint32_t)mt * n2);
@@ -145,10 +163,11 @@ __host__ inline int level_fused_fill_desc(LevelFusedArgs* p) {
       a1l = a1h + plane;
       b_grp = 2u * (uint32_t)p->N2 * 16u;
       b_addr = w_base + L.off_w_out + ((uint32_t)k * G2 + v0) * b_grp;
+      b_lbo = b_grp;
     }
     p->desc[3 * e + 0] = lf_desc_lo(a0, a1h - a0);                    // a_hi
     p->desc[3 * e + 1] = lf_desc_lo(a0 + plane, a1l - (a0 + plane));  // a_lo
-    p->desc[3 * e + 2] = lf_desc_lo(b_addr, b_grp);                   // [w_hi | w_lo]
+    p->desc[3 * e + 2] = lf_desc_lo(b_addr, b_lbo);                   // [w_hi | w_lo]
   }
   return 0;
 }
@@ -167,7 +186,9 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
   uint64_t* bar_ready = bars;        // [2] workers -> MMA: branch br's next layer input is complete (count 384)
   uint64_t* bar_acc = bars + 2;      // [2][2] MMA -> workers: accumulator (branch, M-tile) is complete
   uint64_t* bar_w = bars + 6;        // weights landed
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* bar_a1 = bars + 7;       // [2] workers -> MMA: branch br's first-conv output of the NEXT item is stored
+  uint64_t* bar_fo = bars + 9;       // [2] MMA -> workers: film_out accumulator (M-tile) is complete
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 12);
   float* s_sig = reinterpret_cast<float*>(smem + L.off_sig);   // [2][kLfRows]: index i <-> time t0 - 10 + i
   float* s_par = reinterpret_cast<float*>(smem + L.off_par);
   float* s_bout = s_par + 2 * kLfParPerBranch * 32;
@@ -182,9 +203,13 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
     mbar_init(bar_ready + 1, kLfWorkers);
     for (int i = 0; i < 4; ++i) mbar_init(bar_acc + i, 1);
     mbar_init(bar_w, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_a1 + i, kLfWorkers);
+      mbar_init(bar_fo + i, 1);
+    }
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(s_tmem, 256);
+  if (warp == 12) tmem_alloc(s_tmem, 512);  // 4 chain accumulators (256 columns) + 2 film_out accumulators
   // zero the K-padding strip (never written again) and the buffers (stale rows must stay finite)
   for (uint32_t i = tid; i < (4u * buf_bytes + strip) / 16u; i += kLfThreads)
     reinterpret_cast<uint4*>(smem + buf_off0)[i] = make_uint4(0, 0, 0, 0);
@@ -239,8 +264,8 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
       const uint32_t base4 = smem_u32(smem) >> 4;
       const uint64_t desc_hi = umma_desc(0, 0, 128) & 0xFFFFFFFF00000000ull;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-      const uint32_t n1 = 3u * (uint32_t)(Gp / 2), n2 = 3u * (uint32_t)G;
-      uint32_t ready_phase0 = 0u, ready_phase1 = 0u;
+      const uint32_t n1 = (3u * (uint32_t)G + 1u) / 2u, n2 = 3u * (uint32_t)G;  // chunks per M-tile (level_fused_fill_desc)
+      uint32_t ready_phase0 = 0u, ready_phase1 = 0u, a1_phase = 0u;
       // one M-tile: a_hi x [w_hi | w_lo] -> columns [0, 2N), a_lo x w_hi -> [0, N)
       auto issue_mtile = [&](uint32_t d_tmem, uint32_t& di, uint32_t n_chunks, uint32_t idesc_wide, uint32_t idesc_half) {
         uint32_t accum = 0u;
@@ -260,7 +285,9 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         for (int layer = 0; layer < 3; ++layer) {      // a1 (X) -> a2 (Y) -> y (X) -> h (Y), branches interleaved
           for (int br = 0; br < 2; ++br) {
             if (leader && tl_it == 3) FSVC_TL(63, 1 + (layer * 2 + br) * 3);
-            if (br == 0) {
+            if (layer == 0) {  // the first conv's output was stored during the previous item (own barrier)
+              mbar_wait2(bar_a1 + br, a1_phase);
+            } else if (br == 0) {
               mbar_wait2(bar_ready, ready_phase0);
               ready_phase0 ^= 1u;
             } else {
@@ -285,9 +312,10 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         tc_fence_after();
         if (leader && tl_it == 3) FSVC_TL(63, 20);
         for (int mt = 0; mt < 2; ++mt) {
-          issue_mtile(tmem_u + (uint32_t)mt * 128u, di, n2, idesc_oc, idesc_oh);
-          if (leader) umma_commit(bar_acc + mt);
+          issue_mtile(tmem_u + 256u + (uint32_t)mt * 128u, di, n2, idesc_oc, idesc_oh);
+          if (leader) umma_commit(bar_fo + mt);
         }
+        a1_phase ^= 1u;
         if (leader && tl_it == 3) FSVC_TL(63, 21);
       }
       __syncwarp();
@@ -298,12 +326,16 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
     uint32_t acc_phase0 = 0u, acc_phase1 = 0u;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     griddep_wait();  // the outputs of this kernel may still be read by the previous forward's kernels
-    // raw signal windows of both branches (index i <-> branch i / kLfRows, time t0 - 10 + i % kLfRows): this thread's
-    // <= 2 samples of the NEXT item are requested an item ahead, so their latency is off the item's critical path
-    // (measured: 0.8 of an item's 11.4 us went to this load; 187 -> 174 us per launch.  Also computing the next item's
-    // first conv into registers under this item's second layer measured slower, 179 us: the extra barrier and work
-    // delay the epilogues the tensor core is waiting for)
+    // Software pipeline over items.  The first conv of an item (a1 = Conv3_d1(lrelu(x)) on the CUDA cores, stored as
+    // lrelu(a1), rows t0-8 .. t0+247) is computed at the END of the previous item, after its last chain layer has been
+    // drained (the X buffers are free then) and BEFORE its film_out accumulators are drained: the tensor core goes
+    // from this item's film_out straight to the next item's second conv while the workers store gamma | beta.
+    // film_out has its own TMEM columns and barriers for that.  The raw signal windows of both branches (index i <->
+    // branch i / kLfRows, time t0 - 10 + i % kLfRows) are requested an item before they are staged.  Measured before:
+    // 0.8 us signal load + 0.8 us first conv at the start and 1.8 us gamma | beta drain at the end of an 11.4 us item,
+    // all with the tensor core idle.
     float sig_pre[2];
+    uint32_t fo_phase = 0u;
     auto prefetch_signals = [&](int item) {
       const int bl = item / p.n_tiles, b = p.b_off + bl, t0 = (item - bl * p.n_tiles) * kLfValid;
 #pragma unroll
@@ -314,18 +346,13 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
         sig_pre[k] = (i < 2 * kLfRows && t >= 0 && t < p.T) ? __ldg(p.sig[br] + (long long)b * p.T + t) : 0.f;
       }
     };
-    if ((int)blockIdx.x < n_items) prefetch_signals(blockIdx.x);
-    int tl_it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl_it) {
-      const int bl = item / p.n_tiles, b = p.b_off + bl, t0 = (item - bl * p.n_tiles) * kLfValid;
-      if (tid == 0 && tl_it == 3) FSVC_TL(63, 24);
+    auto first_conv = [&](int item) {  // stage the item's signals, compute + store a1 of both branches, release the MMAs
+      const int bl = item / p.n_tiles, t0 = (item - bl * p.n_tiles) * kLfValid;
 #pragma unroll
       for (int k = 0; k < 2; ++k)
         if (tid + k * kLfWorkers < 2 * kLfRows) s_sig[tid + k * kLfWorkers] = sig_pre[k];
       named_bar_sync(1, kLfWorkers);
       if (item + (int)gridDim.x < n_items) prefetch_signals(item + gridDim.x);
-      if (tid == 0 && tl_it == 3) FSVC_TL(63, 25);
-      // ---- a1 = Conv3_d1(lrelu(x)) on the CUDA cores, stored as lrelu(a1): rows time t0-8 .. t0+247 ----
       for (int br = 0; br < 2; ++br) {
         const float* sg = s_sig + br * kLfRows;
         const float* par = s_par + br * kLfParPerBranch * 32;
@@ -352,9 +379,17 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           split_store(dst + (uint32_t)g * strip + (uint32_t)(tau + kLfHalo) * 16u, plane, v);
         }
         fence_proxy_async();
-        mbar_arrive(bar_ready + br);
-        if (tid == 0 && tl_it == 3) FSVC_TL(63, 26 + br);
+        mbar_arrive(bar_a1 + br);
       }
+    };
+    if ((int)blockIdx.x < n_items) {
+      prefetch_signals(blockIdx.x);
+      first_conv(blockIdx.x);
+    }
+    int tl_it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++tl_it) {
+      const int bl = item / p.n_tiles, b = p.b_off + bl, t0 = (item - bl * p.n_tiles) * kLfValid;
+      if (tid == 0 && tl_it == 3) FSVC_TL(63, 24);
       // ---- three tensor-core layers per branch, branches interleaved:
       //      TMEM -> (hi + lo halves, bias, residual, activation, zero padding) -> bf16 hi|lo -> smem ----
       for (int layer = 0; layer < 3; ++layer) {
@@ -408,14 +443,16 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           if (tid == 0 && tl_it == 3) FSVC_TL(63, 30 + (layer * 2 + br) * 3);
         }
       }
+      // (the residual of layer 1 was the last reader of this item's signals, the FiLM conv's MMAs the last of X)
+      if (item + (int)gridDim.x < n_items) first_conv(item + gridDim.x);
       if (tid == 0 && tl_it == 3) FSVC_TL(63, 46);
       // ---- merged film_out: gamma | beta rows straight to HBM ----
       for (int mt = 0; mt < 2; ++mt) {
-        mbar_wait2(bar_acc + mt, acc_phase0);
+        mbar_wait2(bar_fo + mt, fo_phase);
         tc_fence_after();
         const int tau = 128 * mt + q * 32 + lane, t = t0 + tau;
         const bool ok = tau < kLfValid && t < p.T;
-        const uint32_t tbase = tmem + (uint32_t)mt * 128u + lane_addr;
+        const uint32_t tbase = tmem + 256u + (uint32_t)mt * 128u + lane_addr;
         for (int g = gsel; g < 2 * G; g += 3) {
           float v[8], w[8];
           tmem_ld8(tbase + (uint32_t)(g * 8), v);
@@ -429,10 +466,9 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           }
         }
       }
-      acc_phase0 ^= 1u;
+      fo_phase ^= 1u;
       tc_fence_before();
       if (tid == 0 && tl_it == 3) FSVC_TL(63, 48);
-      // (the next item's first MMAs are gated by bar_ready, which every worker arrives on only after this point)
     }
   }
   tc_fence_before();
@@ -440,7 +476,7 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
   if (tid == 0) FSVC_TL(63, 40);
   if (warp == 12) {
     __syncwarp();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
