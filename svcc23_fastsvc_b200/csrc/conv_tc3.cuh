@@ -48,6 +48,7 @@ struct Tc3Cfg {
   int n_prob;  // 1 or 2 problems (blockIdx.x % n_prob); problem 1 = problem 0 + the pointer deltas below
   int B, m_tiles;
   int b_lo, b_hi;  // utterances [b_lo, b_hi) of the batch are processed by this launch (normally 0, B)
+  int cta0;        // hetero launches: CTAs per N tile of problem 0 (problem 1 gets the rest); 0 = equal interleaved split
   int nsub;       // epilogue sub-tile width (channels, multiple of 8, <= 32)
   int a_slots;    // depth of the A ring (1..3)
   int scr_pitch;  // floats per row of the per-warp statistics scratch (12 or 20)
@@ -302,14 +303,19 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
   uint8_t* const smem = smem_raw;
   const Tc3Cfg& c = L.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int prob = blockIdx.x % c.n_prob;
+  // problem / N tile / CTA index of this block.  Two problems normally interleave and share the grid equally; a hetero
+  // launch may give them different shares (cta0 > 0: the first cta0 * n_ntiles blocks belong to problem 0) when one
+  // problem's items cost more than the other's
+  const int g_nt = L.a.n_ntiles;
+  const int split0 = c.cta0 * g_nt;
+  const int prob = c.cta0 > 0 ? ((int)blockIdx.x >= split0 ? 1 : 0) : (int)(blockIdx.x % c.n_prob);
   const Tc2Args& a = (L.hetero && prob == 1) ? L.b : L.a;
-  const int rest = blockIdx.x / c.n_prob;
-  const int nt = rest % a.n_ntiles;
+  const int rest = c.cta0 > 0 ? (prob ? (int)blockIdx.x - split0 : (int)blockIdx.x) : (int)(blockIdx.x / c.n_prob);
+  const int nt = rest % g_nt;
   // items (utterance, 128-step tile) of this CTA: one contiguous range -- neighbouring tiles share their halo rows
   // in L2 and the utterance (hence the InstanceNorm affine in shared memory) changes at most a few times per CTA
-  const int n_cta = gridDim.x / (c.n_prob * a.n_ntiles);
-  const int cta = rest / a.n_ntiles;
+  const int n_cta = c.cta0 > 0 ? (prob ? ((int)gridDim.x - split0) / g_nt : c.cta0) : (int)(gridDim.x / (c.n_prob * g_nt));
+  const int cta = rest / g_nt;
   const int n_all = (c.b_hi - c.b_lo) * c.m_tiles, item_lo = c.b_lo * c.m_tiles;
   const int first = item_lo + (int)((long long)cta * n_all / n_cta);
   const int n_m = item_lo + (int)((long long)(cta + 1) * n_all / n_cta);
