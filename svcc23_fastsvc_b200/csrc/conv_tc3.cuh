@@ -53,7 +53,7 @@ struct Tc3Cfg {
   int a_slots;    // depth of the A ring (1..3)
   int scr_pitch;  // floats per row of the per-warp statistics scratch (12 or 20)
   uint32_t a_bytes, b_bytes;  // per ring slot
-  uint32_t off_w, off_a, off_b, off_scr, off_pa, off_fin, off_tab, off_stg, off_bar, total;
+  uint32_t off_w, off_a, off_b, off_scr, off_pa, off_bias, off_fin, off_tab, off_stg, off_bar, total;
   uint32_t stg_bytes;  // one slot of the transform's raw-row staging ring (a chunk: kXW warps x CH tasks x 1 KB)
   int stg_depth;       // chunks in flight (ring of stg_depth + 1 slots)
   int cpw;             // tasks per transform warp and chunk (<= kTc3ChunkItems): smaller chunks = smaller staging slots
@@ -111,17 +111,63 @@ __device__ __forceinline__ void ldg2_pred(const float4* p, uint32_t ok, float4& 
       : "+f"(x.x), "+f"(x.y), "+f"(x.z), "+f"(x.w), "+f"(y.x), "+f"(y.y), "+f"(y.z), "+f"(y.w)
       : "l"(p), "r"(ok));
 }
+// ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 do two IEEE fp32 operations per issued instruction).
+// The transform and epilogue roles are bound by instruction issue (4 warps per scheduler, ~0.55 issue slots per cycle in
+// the last stage), so every pair of scalar operations folded into one packed instruction is time, at identical results.
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float c0, float c1) {  // x = x * a + c
+  asm("{\n.reg .b64 x, a, c;\nmov.b64 x, {%0,%1};\nmov.b64 a, {%2,%3};\nmov.b64 c, {%4,%5};\n"
+      "fma.rn.f32x2 x, x, a, c;\nmov.b64 {%0,%1}, x;\n}"
+      : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1) {  // x += a
+  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%0,%1};\nmov.b64 a, {%2,%3};\nadd.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
+      : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void sub2(float& d0, float& d1, float x0, float x1, float a0, float a1) {  // d = x - a
+  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%5};\nsub.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(x0), "f"(x1), "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float x0, float x1, float s) {  // d = x * s
+  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%4};\nmul.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(x0), "f"(x1), "f"(s));
+}
+__device__ __forceinline__ void fma2_acc(float& c0, float& c1, float a0, float a1, float b0, float b1) {  // c += a * b
+  asm("{\n.reg .b64 x, a, c;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%5};\nmov.b64 c, {%0,%1};\n"
+      "fma.rn.f32x2 c, x, a, c;\nmov.b64 {%0,%1}, c;\n}"
+      : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// LeakyReLU of a pair, slope in (0, 1): max(x, x * slope)
+__device__ __forceinline__ void lrelu2(float& x0, float& x1, float slope) {
+  float m0, m1;
+  mul2(m0, m1, x0, x1, slope);
+  x0 = fmaxf(x0, m0);
+  x1 = fmaxf(x1, m1);
+}
+// x * a + c over 8 values, a | c as two float4 each
+__device__ __forceinline__ void affine8(float (&v)[8], const float4& a0, const float4& a1, const float4& c0, const float4& c1) {
+  fma2(v[0], v[1], a0.x, a0.y, c0.x, c0.y);
+  fma2(v[2], v[3], a0.z, a0.w, c0.z, c0.w);
+  fma2(v[4], v[5], a1.x, a1.y, c1.x, c1.y);
+  fma2(v[6], v[7], a1.z, a1.w, c1.z, c1.w);
+}
+__device__ __forceinline__ void lrelu8(float (&v)[8], float slope) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) lrelu2(v[2 * e], v[2 * e + 1], slope);
+}
+// bf16 hi|lo split of a pair: hi = bf16(x) (round to nearest even), lo = bf16(x - hi); the subtraction is exact.
+// (One conversion, a shift and a mask to widen hi again, one packed subtract, one conversion: 5 instructions per pair;
+//  through __nv_bfloat162 the compiler unpacked and repacked the halves with four extra permutes.)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  float d0, d1;
+  sub2(d0, d1, x0, x1, __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+}
 // bf16 hi|lo split of 8 fp32 values, stored as two 16-byte chunks (32-bit shared-space addresses)
 __device__ __forceinline__ void split_store_s(uint32_t addr, uint32_t plane, const float (&v)[8]) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
-  }
+  for (int e = 0; e < 4; ++e) split_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
   sts128(addr, make_uint4(hi[0], hi[1], hi[2], hi[3]));
   sts128(addr + plane, make_uint4(lo[0], lo[1], lo[2], lo[3]));
 }
@@ -153,13 +199,7 @@ __device__ __forceinline__ void cp_async_wait_n(int n) {
 __device__ __forceinline__ void split_bf16(const float (&v)[8], uint4& hi, uint4& lo) {
   uint32_t h4[4], l4[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-    h4[e] = *reinterpret_cast<const uint32_t*>(&h);
-    l4[e] = *reinterpret_cast<const uint32_t*>(&l);
-  }
+  for (int e = 0; e < 4; ++e) split_pair(v[2 * e], v[2 * e + 1], h4[e], l4[e]);
   hi = make_uint4(h4[0], h4[1], h4[2], h4[3]);
   lo = make_uint4(l4[0], l4[1], l4[2], l4[3]);
 }
@@ -167,13 +207,7 @@ __device__ __forceinline__ void split_bf16(const float (&v)[8], uint4& hi, uint4
 __device__ __forceinline__ void split_store_p(uint32_t addr, uint32_t plane, const float (&v)[8], uint32_t pv, uint32_t pz) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
-  }
+  for (int e = 0; e < 4; ++e) split_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
   asm volatile(
       "{\n"
       ".reg .pred pv, pz;\n"
@@ -275,6 +309,8 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
     c->off_pa = off;
     off += pa_bytes;
     off = (off + 15u) & ~15u;
+    c->off_bias = off;
+    off += (uint32_t)((a.N_tile + 3) / 4) * 16u;  // this N tile's bias, staged once by the epilogue warps
     c->off_fin = off;
     off += a.pre_stats ? (uint32_t)(small ? 64 : 192) * 32u : 0u;  // statistics merge scratch: 4 doubles per thread
     c->off_tab = off;
@@ -627,10 +663,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
               if (a.pre_a) {
                 const float4 a0 = lds128f(s_pa + (uint32_t)ch * 4u), a1 = lds128f(s_pa + (uint32_t)ch * 4u + 16u);
                 const float4 c0 = lds128f(s_pc + (uint32_t)ch * 4u), c1 = lds128f(s_pc + (uint32_t)ch * 4u + 16u);
-                v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
-                v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
-                v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
-                v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+                affine8(v, a0, a1, c0, c1);
               }
             }
             if (a.pre_lrelu) {
@@ -913,15 +946,9 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             if (has_aff) {
               const float4 a0 = lds128f(s_pa + aoff[j]), a1 = lds128f(s_pa + aoff[j] + 16u);
               const float4 c0 = lds128f(s_pc + aoff[j]), c1 = lds128f(s_pc + aoff[j] + 16u);
-              v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
-              v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
-              v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
-              v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+              affine8(v, a0, a1, c0, c1);
             }
-            if (a.pre_lrelu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
-            }
+            if (a.pre_lrelu) lrelu8(v, a.slope);  // slope in (0, 1)
             uint4 hi, lo;
             split_bf16(v, hi, lo);
             const int sr = s_first + rl[j];
@@ -1034,15 +1061,9 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
               if (has_aff) {
                 const float4 a0 = lds128f(s_pa + aoff[j]), a1 = lds128f(s_pa + aoff[j] + 16u);
                 const float4 c0 = lds128f(s_pc + aoff[j]), c1 = lds128f(s_pc + aoff[j] + 16u);
-                v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
-                v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
-                v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
-                v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+                affine8(v, a0, a1, c0, c1);
               }
-              if (a.pre_lrelu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
-              }
+              if (a.pre_lrelu) lrelu8(v, a.slope);  // slope in (0, 1)
               split_store_p(sA + soff[j], plane, v, in_strip & real, in_strip & ~real);
             }
           }
@@ -1146,15 +1167,9 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
               const uint32_t ca = (uint32_t)g * 32u;
               const float4 a0 = lds128f(s_pa + ca), a1 = lds128f(s_pa + ca + 16u);
               const float4 c0 = lds128f(s_pc + ca), c1 = lds128f(s_pc + ca + 16u);
-              v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
-              v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
-              v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
-              v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+              affine8(v, a0, a1, c0, c1);
             }
-            if (a.pre_lrelu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
-            }
+            if (a.pre_lrelu) lrelu8(v, a.slope);  // slope in (0, 1)
           }
           uint4 hi, lo;
           split_bf16(v, hi, lo);
@@ -1273,15 +1288,9 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             const uint32_t ca = (uint32_t)(e.w >> 16) * 32u;
             const float4 a0 = lds128f(s_pa + ca), a1 = lds128f(s_pa + ca + 16u);
             const float4 c0 = lds128f(s_pc + ca), c1 = lds128f(s_pc + ca + 16u);
-            v[0] = fmaf(v[0], a0.x, c0.x); v[1] = fmaf(v[1], a0.y, c0.y);
-            v[2] = fmaf(v[2], a0.z, c0.z); v[3] = fmaf(v[3], a0.w, c0.w);
-            v[4] = fmaf(v[4], a1.x, c1.x); v[5] = fmaf(v[5], a1.y, c1.y);
-            v[6] = fmaf(v[6], a1.z, c1.z); v[7] = fmaf(v[7], a1.w, c1.w);
+            affine8(v, a0, a1, c0, c1);
           }
-          if (a.pre_lrelu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * a.slope);  // slope in (0, 1)
-          }
+          if (a.pre_lrelu) lrelu8(v, a.slope);  // slope in (0, 1)
           // rows outside the utterance and the channel padding of the last ci block are zero AFTER the prologue
           const uint32_t in_strip = lane < e.z ? 1u : 0u;
           const uint32_t real = ((unsigned)(ut + (e.w & 0xffff)) < (unsigned)a.T_out && (q.blk * Gb + (e.w >> 16)) * 8 < a.C_in) ? 1u : 0u;
@@ -1335,9 +1344,10 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     const int q = warp & 3, h = ew >> 2;
     const float* bias = a.bias + prob * L.d_bias;
     const float* res = a.res ? a.res + prob * L.d_res : nullptr;
-    const float* gres_w = a.gres_w ? a.gres_w + prob * L.d_gres_w : nullptr;
-    const float* gres_b = a.gres_w ? a.gres_b + prob * L.d_gres_b : nullptr;
-    const float* gres_x = a.gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
+    // generated 1-channel residual (un-fused level-0 chain): only the run-time-width instantiation (NH4 == 0) carries it
+    const float* gres_w = (NH4 == 0 && a.gres_w) ? a.gres_w + prob * L.d_gres_w : nullptr;
+    const float* gres_b = gres_w ? a.gres_b + prob * L.d_gres_b : nullptr;
+    const float* gres_x = gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
     float* raw = a.raw ? a.raw + prob * L.d_raw : nullptr;
     float* out = a.out ? a.out + prob * L.d_out : nullptr;
     const bool has_film = a.gamma != nullptr, has_res = res != nullptr, has_stats = a.stats != nullptr;
@@ -1354,20 +1364,25 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     // operands of one (tile, sub-tile) unit for this thread: requested one unit ahead of their use
     float4 o_res[4], o_ga[4], o_be[4];
     float o_gx = 0.f;
+    // Every tensor of the epilogue is blocked channels-last over the same (utterance, step) rows: one warp-uniform
+    // row-block index per item, then one multiply-add per tensor (the per-tensor 64-bit row arithmetic was ~100 of the
+    // ~520 instructions a warp spent per item).
+    auto row_block = [&](int b, int tile) { return (long long)b * Tp_out + (tile * kTc2M + q * 32); };
     auto load_ops = [&](int b, int tile, int sub) {
       const int t = tile * kTc2M + rl;
       if (t >= a.T_out) return;
       const int nh = unit_nh(sub);
       const int co = co_tile + sub * c.nsub + h * nh;
+      const long long rb = row_block(b, tile);
       if (gres_w) o_gx = __ldg(gres_x + (long long)b * a.T_out + t);
       if (has_res) {
-        const float4* p = reinterpret_cast<const float4*>(res + ntc_row(Tp_out, a.res_ld, b, t) + (co >> 2) * 128);
+        const float4* p = reinterpret_cast<const float4*>(res + rb * a.res_ld + (co >> 2) * 128) + lane;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (NH4 ? j < NH4 : 4 * j < nh) o_res[j] = __ldg(p + 32 * j);
       }
       if (has_film) {
-        const long long ro = ntc_row(Tp_out, a.gb_ld, b, t) + (co >> 2) * 128;
+        const long long ro = rb * a.gb_ld + (co >> 2) * 128 + lane * 4;
         const float4* pg = reinterpret_cast<const float4*>(a.gamma + ro);
         const float4* pb = reinterpret_cast<const float4*>(a.beta + ro);
 #pragma unroll
@@ -1378,6 +1393,16 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
           }
       }
     };
+    // The N tile's bias goes to shared memory once (it is a weight: no need to wait for the predecessor).  Read from
+    // global in every sub-tile it cost a cold L2 round trip per sub-tile: ~0.8 us x 8 sub-tiles in a 192-channel
+    // layer whose CTAs process a single item.
+    const uint32_t s_bias = smem_u32(smem + c.off_bias);
+    {
+      const int et = tid - SH::kE0 * 32;
+      for (int i = et; i < nvalid; i += kTc3EpiThreads)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias + 4u * i), "f"(__ldg(bias + co_tile + i)) : "memory");
+      named_bar_sync(3, kTc3EpiThreads);
+    }
     griddep_wait();  // before the first operand load and the first store
     if (ew == 0 && lane == 0) FSVC_TL(L.tl_slot, 37);
     int b = first / c.m_tiles, tile = first - b * c.m_tiles;
@@ -1395,8 +1420,9 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       const int t = t0 + rl;
       const bool ok = t < a.T_out;
       const int n_rows_seg = min(32, a.T_out - (t0 + q * 32));
-      float* raw_row = raw ? raw + ntc_row(Tp_out, a.raw_ld, b, t) : nullptr;
-      float* out_row = out ? out + ntc_row(Tp_out, a.out_ld, b, t) : nullptr;
+      const long long rb = row_block(b, tile);
+      float* raw_row = raw ? raw + rb * a.raw_ld + lane * 4 : nullptr;
+      float* out_row = out ? out + rb * a.out_ld + lane * 4 : nullptr;
       float2* st_row = has_stats ? a.stats + ((long long)b * a.n_seg + (t0 >> 5) + q) * a.C_out : nullptr;
       if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 48);
       mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
@@ -1408,25 +1434,30 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         const int nh = unit_nh(sub);
         const int col = sub * c.nsub + h * nh;  // first column inside the N tile
         const int co = co_tile + col;
+        const bool tl_u = ew == 0 && lane == 0 && it == 0 && sub == (n_sub > 1 ? 1 : 0);
+        if (tl_u) FSVC_TL(L.tl_slot, 54);
         float v[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (NH4 ? j < NH4 : 4 * j < nh) tmem_ld4_nowait(tacc + (uint32_t)(col + 4 * j), v + 4 * j);
-        const float4* bp = reinterpret_cast<const float4*>(bias + co);
         float4 b4[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (NH4 ? j < NH4 : 4 * j < nh) b4[j] = __ldg(bp + j);
+          if (NH4 ? j < NH4 : 4 * j < nh) b4[j] = lds128f(s_bias + 4u * (uint32_t)col + 16u * j);
         tmem_ld_wait();
+        if (tl_u) FSVC_TL(L.tl_slot, 55);
         const float gx = o_gx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (NH4 ? j < NH4 : 4 * j < nh) {
-            float x[4] = {v[4 * j] + b4[j].x, v[4 * j + 1] + b4[j].y, v[4 * j + 2] + b4[j].z, v[4 * j + 3] + b4[j].w};
+            float x[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]};
+            add2(x[0], x[1], b4[j].x, b4[j].y);
+            add2(x[2], x[3], b4[j].z, b4[j].w);
             if (has_res && ok) {
-              x[0] += o_res[j].x; x[1] += o_res[j].y; x[2] += o_res[j].z; x[3] += o_res[j].w;
+              add2(x[0], x[1], o_res[j].x, o_res[j].y);
+              add2(x[2], x[3], o_res[j].z, o_res[j].w);
             }
-            if (gres_w) {
+            if (NH4 == 0 && gres_w) {
               const float4 w4 = __ldg(reinterpret_cast<const float4*>(gres_w + co) + j);
               const float4 c4 = __ldg(reinterpret_cast<const float4*>(gres_b + co) + j);
               x[0] += fmaf(w4.x, gx, c4.x); x[1] += fmaf(w4.y, gx, c4.y);
@@ -1434,13 +1465,13 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             }
             if (raw_row && ok) reinterpret_cast<float4*>(raw_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
             if (a.post_lrelu) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], x[e] * a.slope);
+              lrelu2(x[0], x[1], a.slope);
+              lrelu2(x[2], x[3], a.slope);
             }
             if (has_film) {
               if (ok) {
-                x[0] = fmaf(o_ga[j].x, x[0], o_be[j].x); x[1] = fmaf(o_ga[j].y, x[1], o_be[j].y);
-                x[2] = fmaf(o_ga[j].z, x[2], o_be[j].z); x[3] = fmaf(o_ga[j].w, x[3], o_be[j].w);
+                fma2(x[0], x[1], o_ga[j].x, o_ga[j].y, o_be[j].x, o_be[j].y);
+                fma2(x[2], x[3], o_ga[j].z, o_ga[j].w, o_be[j].z, o_be[j].w);
               } else {
                 x[0] = x[1] = x[2] = x[3] = 0.f;
               }
@@ -1449,6 +1480,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
           }
         }
+        if (tl_u) FSVC_TL(L.tl_slot, 56);
         if (a.last_w && ok) {
           // conv_last (Conv1d1x1, fastsvc.py:301,330) on the value just produced: this thread's channels' share of every
           // output channel; the other column half adds its share (two commutative adds onto zero: deterministic)
@@ -1463,6 +1495,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         // request the next unit's operands now; they land while this thread waits for the next accumulator
         if (sub + 1 < n_sub) load_ops(b, tile, sub + 1);
         else if (m + step < n_m) load_ops(nb, ntile, 0);
+        if (tl_u) FSVC_TL(L.tl_slot, 57);
         if (has_stats && n_rows_seg > 0) {
           // (mean, M2) of the stored values over this warp's <= 32 rows, per channel: transpose through the warp's
           // smem scratch (rows 16..31 shifted by 16 floats so the two half-warps read disjoint banks), then lane
@@ -1487,11 +1520,17 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[i]) : "r"(colp + i * pitch_b));
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const float dd = xv[i] - piv;
-                s1 += dd;
-                s2 = fmaf(dd, dd, s2);
+              // even and odd rows accumulate side by side (packed fp32), added at the end: a fixed order
+              float s1b = 0.f, s2b = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                float d0, d1;
+                sub2(d0, d1, xv[i], xv[i + 1], piv, piv);
+                add2(s1, s1b, d0, d1);
+                fma2_acc(s2, s2b, d0, d1, d0, d1);
               }
+              s1 += s1b;
+              s2 += s2b;
             } else {
               for (int i = 0; i < cnt; ++i) {
                 float xi;
@@ -1510,6 +1549,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
             st_row[co + ch] = make_float2(piv + dm, fmaxf(fmaf(-s1, dm, s2), 0.f));
           }
         }
+        if (tl_u) FSVC_TL(L.tl_slot, 58);
       }
       if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 50);
       tc_fence_before();

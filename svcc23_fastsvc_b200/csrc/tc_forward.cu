@@ -287,7 +287,8 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
             p[0].n_ntiles, p[0].w_resident, cfg.a_slots, cfg.stg_depth, cfg.total, grid.x, items);
   // compile-time epilogue width (12 channels per thread) when every sub-tile of every N tile is full
   const int per_thread = cfg.nsub / (small ? 1 : 2);
-  const bool nh3 = per_thread == 12 && p[0].C_out % cfg.nsub == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % cfg.nsub == 0);
+  const bool nh3 = per_thread == 12 && p[0].C_out % cfg.nsub == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % cfg.nsub == 0) &&
+                   !p[0].gres_w;  // the generated residual lives in the run-time-width instantiation only
   const int threads = small ? kTc3ThreadsSmall : kTc3Threads;
 #define FSVC_TC3(K_, NH_, SM_)                                                                               \
   do {                                                                                                      \

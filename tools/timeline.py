@@ -52,6 +52,9 @@ for slot, lab in enumerate(labels[:64]):
               f"arrived {us(9):.2f} barrier {us(46):.2f} issued {us(47):.2f}")
         print(f"            mma: wait-A {us(51):.2f} got-A {us(52):.2f} committed {us(53):.2f}   "
               f"epilogue: wait-acc {us(48):.2f} got-acc {us(49):.2f} stored {us(50):.2f}")
+    if t[54] and t[58]:   # epilogue, first item, second sub-tile (warm code): us since the unit started
+        ru = lambda e: (t[e] - t[54]) / 1e3
+        print(f"    epilogue unit: acc loaded {ru(55):.2f} stored {ru(56):.2f} next operands requested {ru(57):.2f} statistics {ru(58):.2f}")
     tl[slot] = 0
 
 # fused level-0 kernel (slot 63): one steady-state item (the CTA's 4th), microseconds since that item's start
