@@ -245,6 +245,11 @@ __device__ __forceinline__ unsigned long long tl_now() {
   } while (0)
 #endif
 
+template <bool V>
+struct BoolC {
+  static constexpr bool value = V;
+};
+
 enum {  // mbarrier indices
   kBarBFull = 0,     // [2] streamed weight block landed
   kBarBEmpty = 2,    // [2] MMAs that read it completed
@@ -1342,222 +1347,236 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
     // =============================== EPILOGUE ===============================
     const int ew = warp - SH::kE0;
     const int q = warp & 3, h = ew >> 2;
-    const float* bias = a.bias + prob * L.d_bias;
-    const float* res = a.res ? a.res + prob * L.d_res : nullptr;
-    // generated 1-channel residual (un-fused level-0 chain): only the run-time-width instantiation (NH4 == 0) carries it
-    const float* gres_w = (NH4 == 0 && a.gres_w) ? a.gres_w + prob * L.d_gres_w : nullptr;
-    const float* gres_b = gres_w ? a.gres_b + prob * L.d_gres_b : nullptr;
-    const float* gres_x = gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
-    float* raw = a.raw ? a.raw + prob * L.d_raw : nullptr;
-    float* out = a.out ? a.out + prob * L.d_out : nullptr;
-    const bool has_film = a.gamma != nullptr, has_res = res != nullptr, has_stats = a.stats != nullptr;
-    const uint32_t scr = smem_u32(smem + c.off_scr) + (uint32_t)(ew * (32 * c.scr_pitch + 16)) * 4u;
-    const uint32_t scr_row = scr + (uint32_t)(lane * c.scr_pitch) * 4u + (lane >= 16 ? 64u : 0u);
-    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const int step_b = step / c.m_tiles, step_t = step - step_b * c.m_tiles;
-    const int rl = q * 32 + lane;  // row of this thread inside the tile
-    const long long Tp_out = ntc_tp(a.T_out);
+    // Two instantiations of the epilogue loop: PLAIN (bias, optional residual, optional LeakyReLU, one store: every
+    // conditioning conv, conv_first, the stage residual conv) and the general one (FiLM affine, raw copy, statistics,
+    // folded conv_last, generated residual).  In the wide layers a thread walks 4..8 sub-tiles per item on its own, at
+    // roughly one instruction per 4 cycles: the ~150 predicated-off instructions of the unused options were most of a
+    // plain sub-tile's ~0.5 us.
+    auto epilogue = [&](auto plain_c) {
+      constexpr bool PLAIN = decltype(plain_c)::value;
+      const float* bias = a.bias + prob * L.d_bias;
+      const float* res = a.res ? a.res + prob * L.d_res : nullptr;
+      // generated 1-channel residual (un-fused level-0 chain): only the run-time-width instantiation (NH4 == 0) carries it
+      const float* gres_w = (!PLAIN && NH4 == 0 && a.gres_w) ? a.gres_w + prob * L.d_gres_w : nullptr;
+      const float* gres_b = gres_w ? a.gres_b + prob * L.d_gres_b : nullptr;
+      const float* gres_x = gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
+      float* raw = (!PLAIN && a.raw) ? a.raw + prob * L.d_raw : nullptr;
+      float* out = a.out ? a.out + prob * L.d_out : nullptr;
+      const bool has_film = !PLAIN && a.gamma != nullptr, has_res = res != nullptr, has_stats = !PLAIN && a.stats != nullptr;
+      const bool has_last = !PLAIN && a.last_w != nullptr;
+      const uint32_t scr = smem_u32(smem + c.off_scr) + (uint32_t)(ew * (32 * c.scr_pitch + 16)) * 4u;
+      const uint32_t scr_row = scr + (uint32_t)(lane * c.scr_pitch) * 4u + (lane >= 16 ? 64u : 0u);
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      const int step_b = step / c.m_tiles, step_t = step - step_b * c.m_tiles;
+      const int rl = q * 32 + lane;  // row of this thread inside the tile
+      const long long Tp_out = ntc_tp(a.T_out);
 
-    // channels of this thread in sub-tile `sub`: nh (multiple of 4), starting at column sub*nsub + h*nh
-    auto unit_nh = [&](int sub) { return NH4 ? 4 * NH4 : (min(c.nsub, nvalid - sub * c.nsub) / SH::kEH); };
+      // channels of this thread in sub-tile `sub`: nh (multiple of 4), starting at column sub*nsub + h*nh
+      auto unit_nh = [&](int sub) { return NH4 ? 4 * NH4 : (min(c.nsub, nvalid - sub * c.nsub) / SH::kEH); };
 
-    // operands of one (tile, sub-tile) unit for this thread: requested one unit ahead of their use
-    float4 o_res[4], o_ga[4], o_be[4];
-    float o_gx = 0.f;
-    // Every tensor of the epilogue is blocked channels-last over the same (utterance, step) rows: one warp-uniform
-    // row-block index per item, then one multiply-add per tensor (the per-tensor 64-bit row arithmetic was ~100 of the
-    // ~520 instructions a warp spent per item).
-    auto row_block = [&](int b, int tile) { return (long long)b * Tp_out + (tile * kTc2M + q * 32); };
-    auto load_ops = [&](int b, int tile, int sub) {
-      const int t = tile * kTc2M + rl;
-      if (t >= a.T_out) return;
-      const int nh = unit_nh(sub);
-      const int co = co_tile + sub * c.nsub + h * nh;
-      const long long rb = row_block(b, tile);
-      if (gres_w) o_gx = __ldg(gres_x + (long long)b * a.T_out + t);
-      if (has_res) {
-        const float4* p = reinterpret_cast<const float4*>(res + rb * a.res_ld + (co >> 2) * 128) + lane;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (NH4 ? j < NH4 : 4 * j < nh) o_res[j] = __ldg(p + 32 * j);
+      // operands of one (tile, sub-tile) unit for this thread: requested one unit ahead of their use
+      float4 o_res[4], o_ga[4], o_be[4];
+      float o_gx = 0.f;
+      // Every tensor of the epilogue is blocked channels-last over the same (utterance, step) rows: one warp-uniform
+      // row-block index per item, then one multiply-add per tensor (the per-tensor 64-bit row arithmetic was ~100 of the
+      // ~520 instructions a warp spent per item).
+      // (fits 32 bits: the library refuses batches of 2^31 or more padded steps, tc_forward.cu)
+      const uint32_t Tp32 = (uint32_t)Tp_out;
+      auto row_block = [&](int b, int tile) { return (unsigned long long)((uint32_t)b * Tp32 + (uint32_t)(tile * kTc2M + q * 32)); };
+      auto load_ops = [&](int b, int tile, int sub) {
+        const int t = tile * kTc2M + rl;
+        if (t >= a.T_out) return;
+        const int nh = unit_nh(sub);
+        const int co = co_tile + sub * c.nsub + h * nh;
+        const unsigned long long rb = row_block(b, tile);
+        if (gres_w) o_gx = __ldg(gres_x + (long long)b * a.T_out + t);
+        if (has_res) {
+          const float4* p = reinterpret_cast<const float4*>(res + rb * (uint32_t)a.res_ld + (uint32_t)((co >> 2) * 128)) + lane;
+  #pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (NH4 ? j < NH4 : 4 * j < nh) o_res[j] = __ldg(p + 32 * j);
+        }
+        if (has_film) {
+          const unsigned long long ro = rb * (uint32_t)a.gb_ld + (uint32_t)((co >> 2) * 128 + lane * 4);
+          const float4* pg = reinterpret_cast<const float4*>(a.gamma + ro);
+          const float4* pb = reinterpret_cast<const float4*>(a.beta + ro);
+  #pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (NH4 ? j < NH4 : 4 * j < nh) {
+              o_ga[j] = __ldg(pg + 32 * j);
+              o_be[j] = __ldg(pb + 32 * j);
+            }
+        }
+      };
+      // The N tile's bias goes to shared memory once (it is a weight: no need to wait for the predecessor).  Read from
+      // global in every sub-tile it cost a cold L2 round trip per sub-tile: ~0.8 us x 8 sub-tiles in a 192-channel
+      // layer whose CTAs process a single item.
+      const uint32_t s_bias = smem_u32(smem + c.off_bias);
+      {
+        const int et = tid - SH::kE0 * 32;
+        for (int i = et; i < nvalid; i += kTc3EpiThreads)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias + 4u * i), "f"(__ldg(bias + co_tile + i)) : "memory");
+        named_bar_sync(3, kTc3EpiThreads);
       }
-      if (has_film) {
-        const long long ro = rb * a.gb_ld + (co >> 2) * 128 + lane * 4;
-        const float4* pg = reinterpret_cast<const float4*>(a.gamma + ro);
-        const float4* pb = reinterpret_cast<const float4*>(a.beta + ro);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (NH4 ? j < NH4 : 4 * j < nh) {
-            o_ga[j] = __ldg(pg + 32 * j);
-            o_be[j] = __ldg(pb + 32 * j);
+      griddep_wait();  // before the first operand load and the first store
+      if (ew == 0 && lane == 0) FSVC_TL(L.tl_slot, 37);
+      int b = first / c.m_tiles, tile = first - b * c.m_tiles;
+      if (first < n_m) load_ops(b, tile, 0);
+      int it = 0;
+      for (int m = first; m < n_m; m += step, ++it) {
+        // next item of this CTA (no division in the loop)
+        int nb = b + step_b, ntile = tile + step_t;
+        if (ntile >= c.m_tiles) {
+          ntile -= c.m_tiles;
+          ++nb;
+        }
+        const int t0 = tile * kTc2M;
+        const uint32_t acc = (uint32_t)it & 1u;
+        const int t = t0 + rl;
+        const bool ok = t < a.T_out;
+        const int n_rows_seg = min(32, a.T_out - (t0 + q * 32));
+        const unsigned long long rb = row_block(b, tile);
+        float* raw_row = raw ? raw + rb * (uint32_t)a.raw_ld + lane * 4 : nullptr;
+        float* out_row = out ? out + rb * (uint32_t)a.out_ld + lane * 4 : nullptr;
+        float2* st_row = has_stats ? a.stats + ((long long)b * a.n_seg + (t0 >> 5) + q) * a.C_out : nullptr;
+        if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 48);
+        mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
+        if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 38);
+        if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 49);
+        tc_fence_after();
+        const uint32_t tacc = tmem + acc * acc_stride + lane_addr;
+        for (int sub = 0; sub < n_sub; ++sub) {
+          const int nh = unit_nh(sub);
+          const int col = sub * c.nsub + h * nh;  // first column inside the N tile
+          const int co = co_tile + col;
+          const bool tl_u = ew == 0 && lane == 0 && it == 0 && sub == (n_sub > 1 ? 1 : 0);
+          if (tl_u) FSVC_TL(L.tl_slot, 54);
+          float v[16];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (NH4 ? j < NH4 : 4 * j < nh) tmem_ld4_nowait(tacc + (uint32_t)(col + 4 * j), v + 4 * j);
+          float4 b4[4];
+  #pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (NH4 ? j < NH4 : 4 * j < nh) b4[j] = lds128f(s_bias + 4u * (uint32_t)col + 16u * j);
+          tmem_ld_wait();
+          if (tl_u) FSVC_TL(L.tl_slot, 55);
+          const float gx = o_gx;
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (NH4 ? j < NH4 : 4 * j < nh) {
+              float x[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]};
+              add2(x[0], x[1], b4[j].x, b4[j].y);
+              add2(x[2], x[3], b4[j].z, b4[j].w);
+              if (has_res && ok) {
+                add2(x[0], x[1], o_res[j].x, o_res[j].y);
+                add2(x[2], x[3], o_res[j].z, o_res[j].w);
+              }
+              if (!PLAIN && NH4 == 0 && gres_w) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(gres_w + co) + j);
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(gres_b + co) + j);
+                x[0] += fmaf(w4.x, gx, c4.x); x[1] += fmaf(w4.y, gx, c4.y);
+                x[2] += fmaf(w4.z, gx, c4.z); x[3] += fmaf(w4.w, gx, c4.w);
+              }
+              if (raw_row && ok) reinterpret_cast<float4*>(raw_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
+              if (a.post_lrelu) {
+                lrelu2(x[0], x[1], a.slope);
+                lrelu2(x[2], x[3], a.slope);
+              }
+              if (has_film) {
+                if (ok) {
+                  fma2(x[0], x[1], o_ga[j].x, o_ga[j].y, o_be[j].x, o_be[j].y);
+                  fma2(x[2], x[3], o_ga[j].z, o_ga[j].w, o_be[j].z, o_be[j].w);
+                } else {
+                  x[0] = x[1] = x[2] = x[3] = 0.f;
+                }
+              }
+              if (out_row && ok) reinterpret_cast<float4*>(out_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
+              v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
+            }
           }
+          if (tl_u) FSVC_TL(L.tl_slot, 56);
+          if (has_last && ok) {
+            // conv_last (Conv1d1x1, fastsvc.py:301,330) on the value just produced: this thread's channels' share of every
+            // output channel; the other column half adds its share (two commutative adds onto zero: deterministic)
+            for (int o = 0; o < a.last_co; ++o) {
+              float p = (h == 0) ? __ldg(a.last_b + o) : 0.f;
+  #pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (NH4 ? j < 4 * NH4 : j < nh) p = fmaf(v[j], __ldg(a.last_w + (long long)(co + j) * a.last_co + o), p);
+              atomicAdd(a.last_out + ((long long)b * a.last_co + o) * a.T_out + t, p);
+            }
+          }
+          // request the next unit's operands now; they land while this thread waits for the next accumulator
+          if (sub + 1 < n_sub) load_ops(b, tile, sub + 1);
+          else if (m + step < n_m) load_ops(nb, ntile, 0);
+          if (tl_u) FSVC_TL(L.tl_slot, 57);
+          if (has_stats && n_rows_seg > 0) {
+            // (mean, M2) of the stored values over this warp's <= 32 rows, per channel: transpose through the warp's
+            // smem scratch (rows 16..31 shifted by 16 floats so the two half-warps read disjoint banks), then lane
+            // (half, ch) sums its 16 rows about the segment's first sample and the halves are added.
+            // in_finalize2_kernel / the consumer's transform role merge the segments in double.
+            __syncwarp();
+  #pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (NH4 ? j < NH4 : 4 * j < nh)
+                sts128(scr_row + 16u * j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+            __syncwarp();
+            const int hh = lane >> 4, ch = lane & 15;
+            const int cnt = max(0, min(16, n_rows_seg - 16 * hh));
+            float piv = 0.f, s1 = 0.f, s2 = 0.f;
+            if (ch < nh) {
+              const uint32_t pitch_b = (uint32_t)c.scr_pitch * 4u;
+              const uint32_t colp = scr + (uint32_t)ch * 4u + (uint32_t)hh * (16u * pitch_b + 64u);
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(piv) : "r"(scr + (uint32_t)ch * 4u));
+              if (cnt == 16) {
+                float xv[16];
+  #pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[i]) : "r"(colp + i * pitch_b));
+  #pragma unroll
+                // even and odd rows accumulate side by side (packed fp32), added at the end: a fixed order
+                float s1b = 0.f, s2b = 0.f;
+  #pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                  float d0, d1;
+                  sub2(d0, d1, xv[i], xv[i + 1], piv, piv);
+                  add2(s1, s1b, d0, d1);
+                  fma2_acc(s2, s2b, d0, d1, d0, d1);
+                }
+                s1 += s1b;
+                s2 += s2b;
+              } else {
+                for (int i = 0; i < cnt; ++i) {
+                  float xi;
+                  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xi) : "r"(colp + i * pitch_b));
+                  const float dd = xi - piv;
+                  s1 += dd;
+                  s2 = fmaf(dd, dd, s2);
+                }
+              }
+            }
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+            if (hh == 0 && ch < nh) {
+              float rn = 0.03125f;
+              if (n_rows_seg < 32) rn = __frcp_rn((float)n_rows_seg);  // ragged last segment of an utterance only
+              const float dm = s1 * rn;
+              st_row[co + ch] = make_float2(piv + dm, fmaxf(fmaf(-s1, dm, s2), 0.f));
+            }
+          }
+          if (tl_u) FSVC_TL(L.tl_slot, 58);
+        }
+        if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 50);
+        tc_fence_before();
+        mbar_arrive(bars + kBarAccEmpty + acc);
+        if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 39);
+        b = nb;
+        tile = ntile;
       }
     };
-    // The N tile's bias goes to shared memory once (it is a weight: no need to wait for the predecessor).  Read from
-    // global in every sub-tile it cost a cold L2 round trip per sub-tile: ~0.8 us x 8 sub-tiles in a 192-channel
-    // layer whose CTAs process a single item.
-    const uint32_t s_bias = smem_u32(smem + c.off_bias);
-    {
-      const int et = tid - SH::kE0 * 32;
-      for (int i = et; i < nvalid; i += kTc3EpiThreads)
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias + 4u * i), "f"(__ldg(bias + co_tile + i)) : "memory");
-      named_bar_sync(3, kTc3EpiThreads);
-    }
-    griddep_wait();  // before the first operand load and the first store
-    if (ew == 0 && lane == 0) FSVC_TL(L.tl_slot, 37);
-    int b = first / c.m_tiles, tile = first - b * c.m_tiles;
-    if (first < n_m) load_ops(b, tile, 0);
-    int it = 0;
-    for (int m = first; m < n_m; m += step, ++it) {
-      // next item of this CTA (no division in the loop)
-      int nb = b + step_b, ntile = tile + step_t;
-      if (ntile >= c.m_tiles) {
-        ntile -= c.m_tiles;
-        ++nb;
-      }
-      const int t0 = tile * kTc2M;
-      const uint32_t acc = (uint32_t)it & 1u;
-      const int t = t0 + rl;
-      const bool ok = t < a.T_out;
-      const int n_rows_seg = min(32, a.T_out - (t0 + q * 32));
-      const long long rb = row_block(b, tile);
-      float* raw_row = raw ? raw + rb * a.raw_ld + lane * 4 : nullptr;
-      float* out_row = out ? out + rb * a.out_ld + lane * 4 : nullptr;
-      float2* st_row = has_stats ? a.stats + ((long long)b * a.n_seg + (t0 >> 5) + q) * a.C_out : nullptr;
-      if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 48);
-      mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
-      if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 38);
-      if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 49);
-      tc_fence_after();
-      const uint32_t tacc = tmem + acc * acc_stride + lane_addr;
-      for (int sub = 0; sub < n_sub; ++sub) {
-        const int nh = unit_nh(sub);
-        const int col = sub * c.nsub + h * nh;  // first column inside the N tile
-        const int co = co_tile + col;
-        const bool tl_u = ew == 0 && lane == 0 && it == 0 && sub == (n_sub > 1 ? 1 : 0);
-        if (tl_u) FSVC_TL(L.tl_slot, 54);
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (NH4 ? j < NH4 : 4 * j < nh) tmem_ld4_nowait(tacc + (uint32_t)(col + 4 * j), v + 4 * j);
-        float4 b4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (NH4 ? j < NH4 : 4 * j < nh) b4[j] = lds128f(s_bias + 4u * (uint32_t)col + 16u * j);
-        tmem_ld_wait();
-        if (tl_u) FSVC_TL(L.tl_slot, 55);
-        const float gx = o_gx;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (NH4 ? j < NH4 : 4 * j < nh) {
-            float x[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]};
-            add2(x[0], x[1], b4[j].x, b4[j].y);
-            add2(x[2], x[3], b4[j].z, b4[j].w);
-            if (has_res && ok) {
-              add2(x[0], x[1], o_res[j].x, o_res[j].y);
-              add2(x[2], x[3], o_res[j].z, o_res[j].w);
-            }
-            if (NH4 == 0 && gres_w) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(gres_w + co) + j);
-              const float4 c4 = __ldg(reinterpret_cast<const float4*>(gres_b + co) + j);
-              x[0] += fmaf(w4.x, gx, c4.x); x[1] += fmaf(w4.y, gx, c4.y);
-              x[2] += fmaf(w4.z, gx, c4.z); x[3] += fmaf(w4.w, gx, c4.w);
-            }
-            if (raw_row && ok) reinterpret_cast<float4*>(raw_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
-            if (a.post_lrelu) {
-              lrelu2(x[0], x[1], a.slope);
-              lrelu2(x[2], x[3], a.slope);
-            }
-            if (has_film) {
-              if (ok) {
-                fma2(x[0], x[1], o_ga[j].x, o_ga[j].y, o_be[j].x, o_be[j].y);
-                fma2(x[2], x[3], o_ga[j].z, o_ga[j].w, o_be[j].z, o_be[j].w);
-              } else {
-                x[0] = x[1] = x[2] = x[3] = 0.f;
-              }
-            }
-            if (out_row && ok) reinterpret_cast<float4*>(out_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
-            v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
-          }
-        }
-        if (tl_u) FSVC_TL(L.tl_slot, 56);
-        if (a.last_w && ok) {
-          // conv_last (Conv1d1x1, fastsvc.py:301,330) on the value just produced: this thread's channels' share of every
-          // output channel; the other column half adds its share (two commutative adds onto zero: deterministic)
-          for (int o = 0; o < a.last_co; ++o) {
-            float p = (h == 0) ? __ldg(a.last_b + o) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (NH4 ? j < 4 * NH4 : j < nh) p = fmaf(v[j], __ldg(a.last_w + (long long)(co + j) * a.last_co + o), p);
-            atomicAdd(a.last_out + ((long long)b * a.last_co + o) * a.T_out + t, p);
-          }
-        }
-        // request the next unit's operands now; they land while this thread waits for the next accumulator
-        if (sub + 1 < n_sub) load_ops(b, tile, sub + 1);
-        else if (m + step < n_m) load_ops(nb, ntile, 0);
-        if (tl_u) FSVC_TL(L.tl_slot, 57);
-        if (has_stats && n_rows_seg > 0) {
-          // (mean, M2) of the stored values over this warp's <= 32 rows, per channel: transpose through the warp's
-          // smem scratch (rows 16..31 shifted by 16 floats so the two half-warps read disjoint banks), then lane
-          // (half, ch) sums its 16 rows about the segment's first sample and the halves are added.
-          // in_finalize2_kernel / the consumer's transform role merge the segments in double.
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (NH4 ? j < NH4 : 4 * j < nh)
-              sts128(scr_row + 16u * j, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                                                   __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
-          __syncwarp();
-          const int hh = lane >> 4, ch = lane & 15;
-          const int cnt = max(0, min(16, n_rows_seg - 16 * hh));
-          float piv = 0.f, s1 = 0.f, s2 = 0.f;
-          if (ch < nh) {
-            const uint32_t pitch_b = (uint32_t)c.scr_pitch * 4u;
-            const uint32_t colp = scr + (uint32_t)ch * 4u + (uint32_t)hh * (16u * pitch_b + 64u);
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(piv) : "r"(scr + (uint32_t)ch * 4u));
-            if (cnt == 16) {
-              float xv[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xv[i]) : "r"(colp + i * pitch_b));
-#pragma unroll
-              // even and odd rows accumulate side by side (packed fp32), added at the end: a fixed order
-              float s1b = 0.f, s2b = 0.f;
-#pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                float d0, d1;
-                sub2(d0, d1, xv[i], xv[i + 1], piv, piv);
-                add2(s1, s1b, d0, d1);
-                fma2_acc(s2, s2b, d0, d1, d0, d1);
-              }
-              s1 += s1b;
-              s2 += s2b;
-            } else {
-              for (int i = 0; i < cnt; ++i) {
-                float xi;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(xi) : "r"(colp + i * pitch_b));
-                const float dd = xi - piv;
-                s1 += dd;
-                s2 = fmaf(dd, dd, s2);
-              }
-            }
-          }
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-          if (hh == 0 && ch < nh) {
-            const float rn = n_rows_seg >= 32 ? 0.03125f : __frcp_rn((float)n_rows_seg);
-            const float dm = s1 * rn;
-            st_row[co + ch] = make_float2(piv + dm, fmaxf(fmaf(-s1, dm, s2), 0.f));
-          }
-        }
-        if (tl_u) FSVC_TL(L.tl_slot, 58);
-      }
-      if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 50);
-      tc_fence_before();
-      mbar_arrive(bars + kBarAccEmpty + acc);
-      if (ew == 0 && lane == 0 && it == 0) FSVC_TL(L.tl_slot, 39);
-      b = nb;
-      tile = ntile;
-    }
+    if (!a.gamma && !a.stats && !a.raw && !a.last_w && !(NH4 == 0 && a.gres_w)) epilogue(BoolC<true>{});
+    else epilogue(BoolC<false>{});
   }
   tc_fence_before();
   __syncthreads();

@@ -324,6 +324,9 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
 int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float* lft, const float* spk, float* out,
                 int B, int frames, void* workspace, size_t ws_bytes, cudaStream_t stream, Profiler* prof) {
   WS2 ws;
+  // the kernels index (utterance, step) rows with 32 bits
+  if ((long long)B * ntc_tp(frames * h->hop) >= (1ll << 31))
+    return fail(FSVC_E_INVALID, "batch of %d x %d steps exceeds 2^31 rows", B, frames * h->hop);
   const size_t need = layout_ws2(h, B, frames, workspace, ws_bytes, &ws);
   if (need > ws_bytes) return fail(FSVC_E_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
   Ctx c;
