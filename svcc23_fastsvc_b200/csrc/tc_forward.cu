@@ -514,9 +514,10 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
     c.label = stage_label[i];
     // InstanceNorm: a conv with `film` writes per-segment (mean, M2) partials of its output; the next conv merges
     // them itself while it loads (conv_tc3 transform role) -- no finalize launch in between.
-    // Long utterances (many segments) keep the separate merge kernel: inside the consumer the merge would sit on
-    // every CTA's critical path (measured: +26 us per conv at 500 segments vs a 12 us launch).
-    const bool fold = n_seg <= 128;
+    // Long utterances (many segments) keep the separate merge kernel: inside the consumer the merge sits on every
+    // CTA's critical path and grows with the utterance, the launch does not.  At config 2's 500 segments the two
+    // cost the same (A/B on one box: 1.0779 ms with three finalize launches, 1.0758 ms merged; 41 vs 44 launches).
+    const bool fold = n_seg <= 512;
     int st_w = 0;  // statistics buffer the next producer writes
     auto film = [&](Tc2Args& a) {
       a.gamma = gamma;
