@@ -367,13 +367,15 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
             const float x0 = sg[tau + 9], x1 = sg[tau + 10], x2 = sg[tau + 11];
             const float l0 = fmaxf(x0, x0 * p.slope), l1 = fmaxf(x1, x1 * p.slope), l2 = fmaxf(x2, x2 * p.slope);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 8; e += 2) {  // two channels per packed instruction
               const int c = g * 8 + e;
-              float y = par[kLfC1B * 32 + c];
-              y = fmaf(par[(kLfC1W + 0) * 32 + c], l0, y);
-              y = fmaf(par[(kLfC1W + 1) * 32 + c], l1, y);
-              y = fmaf(par[(kLfC1W + 2) * 32 + c], l2, y);
-              v[e] = fmaxf(y, y * p.slope);
+              float y0 = par[kLfC1B * 32 + c], y1 = par[kLfC1B * 32 + c + 1];
+              fma2_acc(y0, y1, par[(kLfC1W + 0) * 32 + c], par[(kLfC1W + 0) * 32 + c + 1], l0, l0);
+              fma2_acc(y0, y1, par[(kLfC1W + 1) * 32 + c], par[(kLfC1W + 1) * 32 + c + 1], l1, l1);
+              fma2_acc(y0, y1, par[(kLfC1W + 2) * 32 + c], par[(kLfC1W + 2) * 32 + c + 1], l2, l2);
+              lrelu2(y0, y1, p.slope);
+              v[e] = y0;
+              v[e + 1] = y1;
             }
           }
           split_store(dst + (uint32_t)g * strip + (uint32_t)(tau + kLfHalo) * 16u, plane, v);
@@ -414,11 +416,18 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
               tmem_ld8(tbase + (uint32_t)(p.N1 + g * 8), w);
               if (in_seq) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] += w[e] + bias[g * 8 + e];
+                for (int e = 0; e < 8; e += 2) {  // v += w + bias, two channels per packed instruction
+                  add2(w[e], w[e + 1], bias[g * 8 + e], bias[g * 8 + e + 1]);
+                  add2(v[e], v[e + 1], w[e], w[e + 1]);
+                }
                 if (layer == 1) {  // + Conv1x1(x), then the level output y (kept raw for the FiLM conv)
                   const float x = sg[tau + 10];
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] += fmaf(par[kLfR1W * 32 + g * 8 + e], x, par[kLfR1B * 32 + g * 8 + e]);
+                  for (int e = 0; e < 8; e += 2) {
+                    float r0 = par[kLfR1B * 32 + g * 8 + e], r1 = par[kLfR1B * 32 + g * 8 + e + 1];
+                    fma2_acc(r0, r1, par[kLfR1W * 32 + g * 8 + e], par[kLfR1W * 32 + g * 8 + e + 1], x, x);
+                    add2(v[e], v[e + 1], r0, r1);
+                  }
                   if (p.y_dec[br] && tau >= 0 && tau < kLfValid && t % p.dec == 0) {
                     float4* yp = reinterpret_cast<float4*>(p.y_dec[br] + ntc_row(ntc_tp(p.T / p.dec), C, b, t / p.dec) + g * 256);
                     yp[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
                   }
                 } else {
 #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], v[e] * p.slope);
+                  for (int e = 0; e < 8; e += 2) lrelu2(v[e], v[e + 1], p.slope);
                 }
               } else {
 #pragma unroll
@@ -459,7 +468,10 @@ __global__ void __launch_bounds__(kLfThreads, 1) level0_fused_kernel(const __gri
           tmem_ld8(tbase + (uint32_t)(p.N2 + g * 8), w);
           if (ok) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] += w[e] + s_bout[g * 8 + e];
+            for (int e = 0; e < 8; e += 2) {
+              add2(w[e], w[e + 1], s_bout[g * 8 + e], s_bout[g * 8 + e + 1]);
+              add2(v[e], v[e + 1], w[e], w[e + 1]);
+            }
             float4* op = reinterpret_cast<float4*>(p.gb + ntc_row(ntc_tp(p.T), 2 * C, b, t) + g * 256);
             op[0] = make_float4(v[0], v[1], v[2], v[3]);
             op[32] = make_float4(v[4], v[5], v[6], v[7]);

@@ -119,16 +119,62 @@ __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 do two IEEE fp32 operations per issued instruction).
+// The transform and epilogue roles are bound by instruction issue (4 warps per scheduler, ~0.55 issue slots per cycle in
+// the last stage), so every pair of scalar operations folded into one packed instruction is time, at identical results.
+__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float c0, float c1) {  // x = x * a + c
+  asm("{\n.reg .b64 x, a, c;\nmov.b64 x, {%0,%1};\nmov.b64 a, {%2,%3};\nmov.b64 c, {%4,%5};\n"
+      "fma.rn.f32x2 x, x, a, c;\nmov.b64 {%0,%1}, x;\n}"
+      : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1) {  // x += a
+  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%0,%1};\nmov.b64 a, {%2,%3};\nadd.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
+      : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void sub2(float& d0, float& d1, float x0, float x1, float a0, float a1) {  // d = x - a
+  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%5};\nsub.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(x0), "f"(x1), "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float x0, float x1, float s) {  // d = x * s
+  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%4};\nmul.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
+      : "=f"(d0), "=f"(d1) : "f"(x0), "f"(x1), "f"(s));
+}
+__device__ __forceinline__ void fma2_acc(float& c0, float& c1, float a0, float a1, float b0, float b1) {  // c += a * b
+  asm("{\n.reg .b64 x, a, c;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%5};\nmov.b64 c, {%0,%1};\n"
+      "fma.rn.f32x2 c, x, a, c;\nmov.b64 {%0,%1}, c;\n}"
+      : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// LeakyReLU of a pair, slope in (0, 1): max(x, x * slope)
+__device__ __forceinline__ void lrelu2(float& x0, float& x1, float slope) {
+  float m0, m1;
+  mul2(m0, m1, x0, x1, slope);
+  x0 = fmaxf(x0, m0);
+  x1 = fmaxf(x1, m1);
+}
+// x * a + c over 8 values, a | c as two float4 each
+__device__ __forceinline__ void affine8(float (&v)[8], const float4& a0, const float4& a1, const float4& c0, const float4& c1) {
+  fma2(v[0], v[1], a0.x, a0.y, c0.x, c0.y);
+  fma2(v[2], v[3], a0.z, a0.w, c0.z, c0.w);
+  fma2(v[4], v[5], a1.x, a1.y, c1.x, c1.y);
+  fma2(v[6], v[7], a1.z, a1.w, c1.z, c1.w);
+}
+__device__ __forceinline__ void lrelu8(float (&v)[8], float slope) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) lrelu2(v[2 * e], v[2 * e + 1], slope);
+}
+// bf16 hi|lo split of a pair: hi = bf16(x) (round to nearest even), lo = bf16(x - hi); the subtraction is exact.
+// (One conversion, a shift and a mask to widen hi again, one packed subtract, one conversion: 5 instructions per pair;
+//  through __nv_bfloat162 the compiler unpacked and repacked the halves with four extra permutes.)
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  float d0, d1;
+  sub2(d0, d1, x0, x1, __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(d1), "f"(d0));
+}
 __device__ __forceinline__ void split_store(uint8_t* dst, uint32_t plane, const float (&v)[8]) {
   uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-    const float2 hf = __bfloat1622float2(h);
-    const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
-  }
+  for (int e = 0; e < 4; ++e) split_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
   *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(dst + plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
