@@ -516,8 +516,9 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
     // them itself while it loads (conv_tc3 transform role) -- no finalize launch in between.
     // Long utterances (many segments) keep the separate merge kernel: inside the consumer the merge sits on every
     // CTA's critical path and grows with the utterance, the launch does not.  At config 2's 500 segments the two
-    // cost the same (A/B on one box: 1.0779 ms with three finalize launches, 1.0758 ms merged; 41 vs 44 launches).
-    const bool fold = n_seg <= 512;
+    // cost the same (A/B on one box: 1.0779 ms with three finalize launches, 1.0758 ms merged, each conv ~10 us longer);
+    // the separate kernel is kept there so that a conv launch's time is the conv's.
+    const bool fold = n_seg <= 128;
     int st_w = 0;  // statistics buffer the next producer writes
     auto film = [&](Tc2Args& a) {
       a.gamma = gamma;
