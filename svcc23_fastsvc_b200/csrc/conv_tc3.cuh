@@ -64,6 +64,7 @@ struct Tc3Launch {
   Tc2Args b;   // hetero launches: problem 1's own argument block (same shapes and tiling, different prologue /
   int hetero;  // epilogue flags and tensors), instead of pointer deltas against problem 0
   long long d_in, d_w, d_bias, d_gen_w, d_gen_b, d_res, d_gres_w, d_gres_b, d_gres_x, d_raw, d_out;  // elements
+  long long d_in_pl, d_out_pl;  // 16-byte chunks
   Tc3Cfg c;
   int tl_slot;  // launch index inside the forward (event timeline builds only)
 };
@@ -215,7 +216,7 @@ enum {  // mbarrier indices
 // cpw_force = 4 / 6: lean transform (MODE 3 / 4 / 5).  bulk = true (MODE 3 / 4): a staging slot holds the 6 aligned
 // 32-row blocks of the input that cover an item's window, filled by cp.async.bulk.
 __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool small = false, int cpw_force = 0,
-                                   bool bulk = false) {
+                                   bool bulk = false, bool direct = false) {
   const int halo = (K / 2) * a.dil, W = kTc2M + 2 * halo;
   const uint32_t Gb = a.CIB / 8;
   c->a_bytes = 2u * Gb * W * 16u;
@@ -250,6 +251,10 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
     if (cpw_force && pr[2] != 4) continue;
     c->stg_bytes = a.gen_w ? 0u : xw * (uint32_t)c->cpw * 1024u;
     if (bulk) c->stg_bytes = 6u * (uint32_t)(a.CIB >> 2) * 512u;
+    if (direct) {  // MODE 6: the A ring is filled from operand planes, nothing is staged
+      c->stg_bytes = 0u;
+      c->stg_depth = 0;
+    }
     uint32_t off = 0;
     c->off_w = off;
     off += w_bytes;
@@ -330,7 +335,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       mbar_init(bars + kBarAccEmpty + i, kTc3EpiThreads);
     }
     for (int i = 0; i < 3; ++i) {
-      mbar_init(bars + kBarAFull + i, kTc3XformThreads);
+      mbar_init(bars + kBarAFull + i, MODE == 6 ? 1 : kTc3XformThreads);  // MODE 6: the loader's expect_tx arrival
       mbar_init(bars + kBarAEmpty + i, 1);
     }
     mbar_init(bars + kBarWFull, 1);
@@ -404,6 +409,45 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
           if (++slot == (uint32_t)ring) {
             slot = 0;
             ++use;
+          }
+        }
+        if (++ltile == c.m_tiles) {
+          ltile = 0;
+          ++lb;
+        }
+      }
+    } else if constexpr (MODE == 6) {
+      // Operand planes (ntc_common.cuh): the window of an item, per 8-channel group and plane, is one contiguous run of
+      // W 16-byte rows in global memory AND in the A slot -- 2 * Gb bulk copies per (item, ci block) fill the slot,
+      // completed on the slot's AFull barrier.  Rows outside the utterance are zeros in the tensor.
+      const uint4* pl = a.in_pl + prob * L.d_in_pl;
+      const uint32_t Gb = (uint32_t)a.CIB >> 3, strip = (uint32_t)W * 16u, plane = Gb * strip;
+      int lb = first / c.m_tiles, ltile = first - lb * c.m_tiles;
+      uint32_t aslot = 0, ause = 0;
+      bool waited = false;
+      for (int m = first; m < n_m; ++m) {
+        const long long row0 = (long long)ltile * kTc2M - halo + kPlPad;
+        for (int blk = 0; blk < a.n_blk; ++blk) {
+          if (!a.w_resident) stream_weights(blk);
+          if (!waited) {
+            griddep_wait();  // first access to the predecessor's output
+            waited = true;
+          }
+          if (ause > 0) mbar_wait2(bars + kBarAEmpty + aslot, (ause + 1) & 1u);
+          const int g0 = blk * (int)Gb, ng = min((int)Gb, (a.C_in >> 3) - g0);
+          uint64_t* bar = bars + kBarAFull + aslot;
+          mbar_expect_tx(bar, 2u * (uint32_t)ng * strip);
+          uint8_t* dst = smem + c.off_a + aslot * c.a_bytes;
+          const uint4* src = pl + ((long long)lb * a.in_pl_G + g0) * a.in_pl_Tp + row0;
+          for (int g = 0; g < ng; ++g) {
+            bulk_g2s(dst + (uint32_t)g * strip, src + (long long)g * a.in_pl_Tp, strip, bar);
+            bulk_g2s(dst + plane + (uint32_t)g * strip, src + (long long)g * a.in_pl_Tp + a.in_pl_lo, strip, bar);
+          }
+          if (tid == 0 && (a.n_blk == 1 ? m - first : blk) < 12 && (a.n_blk == 1 || m == first))
+            FSVC_TL(L.tl_slot, 4 + (a.n_blk == 1 ? m - first : blk));
+          if (++aslot == (uint32_t)c.a_slots) {
+            aslot = 0;
+            ++ause;
           }
         }
         if (++ltile == c.m_tiles) {
@@ -489,7 +533,9 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       __syncwarp();
     }
   } else if (warp >= SH::kX0 && warp < SH::kE0) {
-   if constexpr (GEN) {
+   if constexpr (MODE == 6) {
+    // no transform: the A ring is filled by the row loader from the producer's operand planes
+   } else if constexpr (GEN) {
     // =============================== TRANSFORM ===============================
     const int tt = tid - 32 * SH::kX0;
     const uint32_t smem_base = smem_u32(smem);
@@ -1309,6 +1355,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       const float* gres_b = gres_w ? a.gres_b + prob * L.d_gres_b : nullptr;
       const float* gres_x = gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
       float* raw = (!PLAIN && a.raw) ? a.raw + prob * L.d_raw : nullptr;
+      uint4* out_pl = (PLAIN && a.out_pl) ? a.out_pl + prob * L.d_out_pl : nullptr;  // operand planes (ntc_common.cuh)
       float* out = a.out ? a.out + prob * L.d_out : nullptr;
       const bool has_film = !PLAIN && a.gamma != nullptr, has_res = res != nullptr, has_stats = !PLAIN && a.stats != nullptr;
       const bool has_last = !PLAIN && a.last_w != nullptr;
@@ -1386,6 +1433,11 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         const unsigned long long rb = row_block(b, tile);
         float* raw_row = raw ? raw + rb * (uint32_t)a.raw_ld + lane * 4 : nullptr;
         float* out_row = out ? out + rb * (uint32_t)a.out_ld + lane * 4 : nullptr;
+        // this thread's row in group 0 of the operand planes; pad_rows: 0, or -/+ kPlPad when the thread also owns a
+        // zero row in front of the utterance (first tile, first 8 steps) / behind its last tile
+        uint4* pl_row = out_pl ? out_pl + (long long)b * a.out_pl_G * a.out_pl_Tp + (kPlPad + t) : nullptr;
+        const int pad_rows = !out_pl ? 0 : (tile == 0 && rl < kPlPad) ? -kPlPad
+                                         : (tile == c.m_tiles - 1 && rl >= kTc2M - kPlPad) ? kPlPad : 0;
         float2* st_row = has_stats ? a.stats + ((long long)b * a.n_seg + (t0 >> 5) + q) * a.C_out : nullptr;
         if (ew == 0 && lane == 0 && it == 5) FSVC_TL(L.tl_slot, 48);
         mbar_wait2(bars + kBarAccFull + acc, ((uint32_t)it >> 1) & 1u);
@@ -1440,6 +1492,27 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
                 }
               }
               if (out_row && ok) reinterpret_cast<float4*>(out_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
+              if (PLAIN && pl_row) {
+                // 4 channels = half of a (step, group) chunk in each plane; steps past the utterance's end are zeros
+                float y[4] = {x[0], x[1], x[2], x[3]};
+                if (!ok) {
+                  y[0] = y[1] = y[2] = y[3] = 0.f;
+                } else if (a.out_pl_lrelu) {
+                  lrelu2(y[0], y[1], a.slope);
+                  lrelu2(y[2], y[3], a.slope);
+                }
+                uint32_t h0, l0, h1, l1;
+                split_pair(y[0], y[1], h0, l0);
+                split_pair(y[2], y[3], h1, l1);
+                const int cq = co + 4 * j;
+                uint2* d = reinterpret_cast<uint2*>(pl_row + (long long)(cq >> 3) * a.out_pl_Tp) + ((cq >> 2) & 1);
+                d[0] = make_uint2(h0, h1);
+                d[2 * a.out_pl_lo] = make_uint2(l0, l1);
+                if (pad_rows != 0) {
+                  d[2 * pad_rows] = make_uint2(0u, 0u);
+                  d[2 * (a.out_pl_lo + pad_rows)] = make_uint2(0u, 0u);
+                }
+              }
               v[4 * j] = x[0]; v[4 * j + 1] = x[1]; v[4 * j + 2] = x[2]; v[4 * j + 3] = x[3];
             }
           }

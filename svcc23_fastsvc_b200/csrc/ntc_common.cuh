@@ -58,7 +58,21 @@ struct Tc2Args {
   float* last_out;      // (B, last_co, T_out), time fastest
   int last_co;
   float slope;
+  // ---- operand planes: bf16 hi | lo in the shared-memory operand layout, [B][G][Tp][8 channels] -----------------
+  // A producer whose consumer's prologue is at most a LeakyReLU writes its output split and activated, one 16-byte
+  // chunk per (step, 8-channel group) -- exactly a row of the consumer's K-major A tile -- and the consumer's row
+  // loader bulk-copies an item's window per group and plane straight into the A ring: no transform role (conv_tc3
+  // MODE 6).  Tp = 128 * tiles + 2 * kPlPad rows per (utterance, group): kPlPad zero rows in front of step 0, zeros
+  // from step T to the end (written by the producer), so the conv's zero padding is part of the tensor.
+  const uint4* in_pl;    // consumer: hi plane of the input; the lo plane starts in_pl_lo chunks later
+  long long in_pl_lo;
+  int in_pl_G, in_pl_Tp;  // groups per utterance in the tensor (the utterance stride is G * Tp chunks), rows per group
+  uint4* out_pl;         // producer (plain epilogue): hi plane, group 0 of this conv's first output channel
+  long long out_pl_lo;
+  int out_pl_G, out_pl_Tp;
+  int out_pl_lrelu;      // LeakyReLU before the split (the consumer's prologue, applied once here)
 };
+constexpr int kPlPad = 8;
 
 // Blocked channels-last activation layout of the tensor-core forward: [B][ceil(T/32)][ld/4][32 steps][4 channels].
 // 32 consecutive time steps of one 4-channel group are 512 contiguous bytes, so a warp whose lanes own

@@ -76,7 +76,8 @@ int tc_setup_kernels() {
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
   FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
   FSVC_ATTR(3, 3, false);
   FSVC_ATTR(3, 0, false);
   FSVC_ATTR(1, 3, false);
@@ -103,6 +104,9 @@ struct WS2 {
   float* ydec[2];                // [B][T/s][C0] level-0 output decimated for level 1 (fused level kernel)
 };
 
+// rows per (utterance, 8-channel group) of an operand-plane tensor: whole 128-step tiles + kPlPad zero rows at both ends
+static inline int pl_rows(int T) { return (T + kTc2M - 1) / kTc2M * kTc2M + 2 * kPlPad; }
+
 static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, size_t cap, WS2* ws) {
   Arena ar(base, cap);
   const int n = h->n;
@@ -113,9 +117,12 @@ static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, si
   for (int l = 0; l < n; ++l) {
     T_l /= h->dscale[l];
     const size_t ne = (size_t)B * h->lvl_c[l] * ntc_tp(T_l);
+    // the chain temporaries and H may hold bf16 hi|lo operand planes instead (ntc_common.cuh): C * pl_rows floats per utterance
+    const size_t ne_pl = (size_t)B * h->lvl_c[l] * pl_rows(T_l);
     max_lvl = ne > max_lvl ? ne : max_lvl;
+    max_lvl = ne_pl > max_lvl ? ne_pl : max_lvl;
     for (int br = 0; br < 2; ++br) ws->y[br][l] = ar.get<float>(ne);
-    ws->H[l] = ar.get<float>(2 * ne);
+    ws->H[l] = ar.get<float>(2 * (ne_pl > ne ? ne_pl : ne));
     ws->GB[l] = ar.get<float>(2 * ne);
   }
   for (int br = 0; br < 2; ++br) {
@@ -209,7 +216,7 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     if (x.up != y.up || x.down != y.down || x.dil != y.dil || x.C_in != y.C_in || x.C_out != y.C_out ||
         x.T_out != y.T_out || x.T_in != y.T_in || x.in_ld != y.in_ld || x.CIB != y.CIB || x.n_blk != y.n_blk ||
         x.N_tile != y.N_tile || x.n_ntiles != y.n_ntiles || x.w_resident != y.w_resident || x.gen_w || y.gen_w ||
-        x.pre_stats || y.pre_stats || x.pre_a || y.pre_a) {
+        x.pre_stats || y.pre_stats || x.pre_a || y.pre_a || x.in_pl || y.in_pl || x.out_pl || y.out_pl) {
       c.err = 2;
       return;
     }
@@ -226,12 +233,16 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     L.d_gres_x = x.gres_w ? y.gres_x - x.gres_x : 0;
     L.d_raw = x.raw ? y.raw - x.raw : 0;
     L.d_out = x.out ? y.out - x.out : 0;
+    L.d_in_pl = x.in_pl ? y.in_pl - x.in_pl : 0;
+    L.d_out_pl = x.out_pl ? y.out_pl - x.out_pl : 0;
     // everything that is not a per-problem pointer must agree
     if ((x.up > 1 && x.down > 1) || x.pre_lrelu != y.pre_lrelu || x.post_lrelu != y.post_lrelu || x.gamma != y.gamma || x.stats != y.stats ||
         x.pre_a != y.pre_a || x.up != y.up || x.down != y.down || x.dil != y.dil || x.C_in != y.C_in ||
         x.C_out != y.C_out || x.T_out != y.T_out || x.T_in != y.T_in || x.in_ld != y.in_ld ||
         x.out_ld != y.out_ld || x.res_ld != y.res_ld || (x.res == nullptr) != (y.res == nullptr) ||
-        (x.gen_w == nullptr) != (y.gen_w == nullptr) || (x.gres_w == nullptr) != (y.gres_w == nullptr)) {
+        (x.gen_w == nullptr) != (y.gen_w == nullptr) || (x.gres_w == nullptr) != (y.gres_w == nullptr) ||
+        (x.in_pl == nullptr) != (y.in_pl == nullptr) || (x.out_pl == nullptr) != (y.out_pl == nullptr) ||
+        x.in_pl_lo != y.in_pl_lo || x.out_pl_lo != y.out_pl_lo || x.out_pl_lrelu != y.out_pl_lrelu) {
       c.err = 2;
       return;
     }
@@ -251,12 +262,20 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   const bool small = false;
   // transform variant: 3 / 4 = lean path (direct rows, one ci block, a warp's <= 4 / <= 6 tasks of an item in one chunk)
   int mode = p[0].gen_w ? 1 : (p[0].up > 1 ? 2 : 0);
-  if (mode == 0 && p[0].down == 1 && !getenv("FSVC_NO_LEAN")) {
+  if (mode == 0 && p[0].down == 1 && !p[0].in_pl && !getenv("FSVC_NO_LEAN")) {
     const int ntask = (p[0].CIB / 8) * ((kTc2M + 2 * (K / 2) * p[0].dil + 31) / 32);
     const int rounds = (ntask + 5) / 6;
     const bool bulk = (K / 2) * p[0].dil <= 32;  // the window spans at most 6 aligned 32-row blocks
     if (bulk && rounds <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4, true)) mode = 3;
     else if (bulk && rounds <= 6 && tc3_plan_smem(p[0], K, &cfg, false, 6, true) && cfg.a_slots >= 2) mode = 4;
+  }
+  if (p[0].in_pl) {  // operand planes written by the producer: no transform role
+    if (mode != 0 || p[0].down != 1 || (K / 2) * p[0].dil > kPlPad || p[0].C_in % 8 != 0 || p[0].C_in % p[0].CIB != 0 ||
+        !tc3_plan_smem(p[0], K, &cfg, false, 0, false, true)) {
+      c.err = 3;
+      return;
+    }
+    mode = 6;
   }
   if (mode == 2 && p[0].down == 1 && p[0].up <= 8 && p[0].n_blk == 1 && !getenv("FSVC_NO_LEAN")) {
     const int Wd = kTc2M + 2 * (K / 2) * p[0].dil;
@@ -297,6 +316,7 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     else if (mode == 3) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 3>, grid, threads, cfg.total, c.stream, L); \
     else if (mode == 4) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 4>, grid, threads, cfg.total, c.stream, L); \
     else if (mode == 5) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 5>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 6) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 6>, grid, threads, cfg.total, c.stream, L); \
     else launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 0>, grid, threads, cfg.total, c.stream, L);                \
   } while (0)
   if (K == 3) {
@@ -311,7 +331,7 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     const double BT = (double)(b_hi - b_lo) * a.T_out;
     flops += 2.0 * a.C_in * a.C_out * K * BT;
     elems += a.gen_w ? BT : (double)(b_hi - b_lo) * a.C_in * ((double)a.T_out / a.up);
-    elems += BT * a.C_out * ((a.out ? 1 : 0) + (a.raw ? 1 : 0) + (a.res ? 1 : 0) + (a.gamma ? 2 : 0));
+    elems += BT * a.C_out * ((a.out ? 1 : 0) + (a.out_pl ? 1 : 0) + (a.raw ? 1 : 0) + (a.res ? 1 : 0) + (a.gamma ? 2 : 0));
     if (a.last_w) {  // folded conv_last
       flops += 2.0 * BT * a.C_out * a.last_co;
       elems += BT * a.last_co + (double)a.C_out * a.last_co;
@@ -387,6 +407,22 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
     const int C = h->lvl_c[l];
     c.label = lvl_label[l];
     Tc2Args p[2];
+    bool use_pl = false;
+    const int pl_Tp = pl_rows(T_l);
+    // operand planes of this level: `buf` holds the hi plane [B][G][pl_Tp] chunks, then the lo plane
+    auto planes_out = [&](Tc2Args& a, float* buf, int G, int g0, int lrelu) {
+      a.out_pl = reinterpret_cast<uint4*>(buf) + (long long)g0 * pl_Tp;
+      a.out_pl_lo = (long long)B * G * pl_Tp;
+      a.out_pl_G = G;
+      a.out_pl_Tp = pl_Tp;
+      a.out_pl_lrelu = lrelu;
+    };
+    auto planes_in = [&](Tc2Args& a, const float* buf, int G) {
+      a.in_pl = reinterpret_cast<const uint4*>(buf);
+      a.in_pl_lo = (long long)B * G * pl_Tp;
+      a.in_pl_G = G;
+      a.in_pl_Tp = pl_Tp;
+    };
     if (l == 0 && h->l0_fused) {
       const LevelFusedSmem LF =
           level_fused_smem(C, lw.c2[0].nc_G, lw.c2[0].nc_N, lw.film_out.nc_N);
@@ -470,16 +506,29 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
         p[br].down = dec_in ? 1 : h->dscale[l];
       }
       launch_tc2(c, h, 1, p, 2, "down_r1x1");
+      // d1 -> d2 -> d4 and film_conv -> film_out hand their tensors over as bf16 hi|lo operand planes (the consumer's
+      // prologue is only a LeakyReLU, applied by the producer): d2, d4 and film_out run without a transform role
+      // Only where a CTA sees few items (the layer is a latency chain per item and the transform's turn is a third of
+      // it: level 3 convs 25-37 -> 20-26 us, level 2's film_out 35 -> 29 us); with many items per CTA the layer moves
+      // at the HBM rate either way (level 1: 147 MB in 23 us) and the producer's longer epilogue costs 4 us.
+      const long long lvl_items = 2ll * B * ((T_l + kTc2M - 1) / kTc2M);
+      use_pl = C % 8 == 0 && C % lw.c2[0].tc2.CIB == 0 && C % lw.c4[0].tc2.CIB == 0 && (2 * C) % lw.film_out.tc2.CIB == 0 &&
+               lvl_items <= 6ll * h->num_sms && !getenv("FSVC_NO_PLANES");
       for (int br = 0; br < 2; ++br) {
         p[br] = tc2_args(c, lw.c1[br], dec_in ? ws.ydec[br] : ws.y[br][l - 1], Cp, dec_in ? T_l : T_prev, T_l, 1,
-                         ws.ta[br], C);
+                         use_pl ? nullptr : ws.ta[br], C);
         p[br].down = dec_in ? 1 : h->dscale[l];
         p[br].pre_lrelu = 1;
+        if (use_pl) planes_out(p[br], ws.ta[br], C / 8, 0, 1);
       }
       launch_tc2(c, h, 3, p, 2, "down_d1");
       for (int br = 0; br < 2; ++br) {
-        p[br] = tc2_args(c, lw.c2[br], ws.ta[br], C, T_l, T_l, 2, ws.tb[br], C);
+        p[br] = tc2_args(c, lw.c2[br], ws.ta[br], C, T_l, T_l, 2, use_pl ? nullptr : ws.tb[br], C);
         p[br].pre_lrelu = 1;
+        if (use_pl) {
+          planes_in(p[br], ws.ta[br], C / 8);
+          planes_out(p[br], ws.tb[br], C / 8, 0, 1);
+        }
       }
       launch_tc2(c, h, 3, p, 2, "down_d2");
       for (int br = 0; br < 2; ++br) {
@@ -487,15 +536,18 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
         p[br].pre_lrelu = 1;
         p[br].res = ws.tr[br];
         p[br].res_ld = C;
+        if (use_pl) planes_in(p[br], ws.tb[br], C / 8);
       }
       launch_tc2(c, h, 3, p, 2, "down_d4");
     }
     for (int br = 0; br < 2; ++br) {
-      p[br] = tc2_args(c, lw.film[br], ws.y[br][l], C, T_l, T_l, 1, ws.H[l] + ntc_col(br * C), 2 * C);
+      p[br] = tc2_args(c, lw.film[br], ws.y[br][l], C, T_l, T_l, 1, use_pl ? nullptr : ws.H[l] + ntc_col(br * C), 2 * C);
       p[br].post_lrelu = 1;
+      if (use_pl) planes_out(p[br], ws.H[l], 2 * C / 8, br * (C / 8), 0);  // both branches side by side: 2C/8 groups
     }
     launch_tc2(c, h, 3, p, 2, "film_conv");
     p[0] = tc2_args(c, lw.film_out, ws.H[l], 2 * C, T_l, T_l, 1, ws.GB[l], 2 * C);
+    if (use_pl) planes_in(p[0], ws.H[l], 2 * C / 8);
     launch_tc2(c, h, 3, p, 1, "film_out");
     T_prev = T_l;
   }
