@@ -119,6 +119,23 @@ def test_full_size_properties(precision, golden_index):
     assert abs(ysum - meta["sum64"]) <= 1e-3 * 32 * 16000 * 1e-2 + 1e-4 * abs(meta["sum64"])
 
 
+def test_operand_planes_change_no_bit(golden_index, monkeypatch):
+    """Levels whose CTAs see few items hand d1 -> d2 -> d4 and film_conv -> film_out over as bf16 hi|lo operand planes
+    (conv_tc3 MODE 6: the producer's epilogue applies the consumer's LeakyReLU and split).  Same arithmetic in another
+    place: the waveform must not change by a bit against the transform path (FSVC_NO_PLANES=1)."""
+    for case in ("gen_yaml_b2_f51", "gen_yaml_b32"):
+        meta = golden_index[case]
+        g, params, ppg, sine, lft, spk = _build_generator(meta, "tc_bf16x3")
+        args = [_t(ppg), _t(sine), _t(lft), _t(spk)]
+        with torch.no_grad():
+            monkeypatch.delenv("FSVC_NO_PLANES", raising=False)
+            y_planes = g(*args)
+            monkeypatch.setenv("FSVC_NO_PLANES", "1")
+            y_transform = g(*args)
+            monkeypatch.delenv("FSVC_NO_PLANES", raising=False)
+        assert torch.equal(y_planes, y_transform), case
+
+
 def test_forward_host_matches_device_forward(golden_index):
     meta = golden_index["gen_yaml_b2_f51"]
     g, params, ppg, sine, lft, spk = _build_generator(meta, "auto")
