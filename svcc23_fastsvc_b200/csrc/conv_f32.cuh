@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "fsvc_internal.h"
+#include "packed_f32.cuh"
 
 namespace fsvc {
 
@@ -128,10 +129,24 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_f32_kernel(const ConvArgs
         const float* xp = in_s + ci * W_in + k * a.dil + lane;
 #pragma unroll
         for (int j = 0; j < RT; ++j) xv[j] = xp[32 * j];
+        // two accumulators per packed FMA (same products, same order: bit-identical to the scalar loop): channel pairs
+        // when RC is even, time pairs otherwise
+        if constexpr (RC % 2 == 0) {
 #pragma unroll
-        for (int i = 0; i < RC; ++i)
+          for (int i = 0; i < RC; i += 2)
 #pragma unroll
-          for (int j = 0; j < RT; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+            for (int j = 0; j < RT; ++j) fma2_acc(acc[i][j], acc[i + 1][j], wv[i], wv[i + 1], xv[j], xv[j]);
+        } else if constexpr (RT % 2 == 0) {
+#pragma unroll
+          for (int i = 0; i < RC; ++i)
+#pragma unroll
+            for (int j = 0; j < RT; j += 2) fma2_acc(acc[i][j], acc[i][j + 1], wv[i], wv[i], xv[j], xv[j + 1]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < RC; ++i)
+#pragma unroll
+            for (int j = 0; j < RT; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+        }
       }
     }
   }

@@ -6,6 +6,7 @@
 // (layers/upsample.py:38-74), _feature_affine + LeakyReLU (fastsvc.py:115-140, 56-75), FastSVCDownsampleNet's first
 // conv and 1x1 residual on the raw 1-channel signal (fastsvc.py:164-172, "gen" operands below).
 #pragma once
+#include "packed_f32.cuh"
 #include "tc_prims.cuh"
 
 namespace fsvc {
@@ -133,31 +134,6 @@ __device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 do two IEEE fp32 operations per issued instruction).
-// The transform and epilogue roles are bound by instruction issue (4 warps per scheduler, ~0.55 issue slots per cycle in
-// the last stage), so every pair of scalar operations folded into one packed instruction is time, at identical results.
-__device__ __forceinline__ void fma2(float& x0, float& x1, float a0, float a1, float c0, float c1) {  // x = x * a + c
-  asm("{\n.reg .b64 x, a, c;\nmov.b64 x, {%0,%1};\nmov.b64 a, {%2,%3};\nmov.b64 c, {%4,%5};\n"
-      "fma.rn.f32x2 x, x, a, c;\nmov.b64 {%0,%1}, x;\n}"
-      : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1), "f"(c0), "f"(c1));
-}
-__device__ __forceinline__ void add2(float& x0, float& x1, float a0, float a1) {  // x += a
-  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%0,%1};\nmov.b64 a, {%2,%3};\nadd.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
-      : "+f"(x0), "+f"(x1) : "f"(a0), "f"(a1));
-}
-__device__ __forceinline__ void sub2(float& d0, float& d1, float x0, float x1, float a0, float a1) {  // d = x - a
-  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%5};\nsub.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
-      : "=f"(d0), "=f"(d1) : "f"(x0), "f"(x1), "f"(a0), "f"(a1));
-}
-__device__ __forceinline__ void mul2(float& d0, float& d1, float x0, float x1, float s) {  // d = x * s
-  asm("{\n.reg .b64 x, a;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%4};\nmul.rn.f32x2 x, x, a;\nmov.b64 {%0,%1}, x;\n}"
-      : "=f"(d0), "=f"(d1) : "f"(x0), "f"(x1), "f"(s));
-}
-__device__ __forceinline__ void fma2_acc(float& c0, float& c1, float a0, float a1, float b0, float b1) {  // c += a * b
-  asm("{\n.reg .b64 x, a, c;\nmov.b64 x, {%2,%3};\nmov.b64 a, {%4,%5};\nmov.b64 c, {%0,%1};\n"
-      "fma.rn.f32x2 c, x, a, c;\nmov.b64 {%0,%1}, c;\n}"
-      : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
-}
 // LeakyReLU of a pair, slope in (0, 1): max(x, x * slope)
 __device__ __forceinline__ void lrelu2(float& x0, float& x1, float slope) {
   float m0, m1;

@@ -106,12 +106,12 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_kernel(const WgradArgs 
 #pragma unroll
         for (int k = 0; k < K; ++k) av[q][k] = a_s[(wci + q) * W + p + k * a.dil];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        bsum[r] += gv[r];
+      for (int r = 0; r < 4; r += 2) {  // output-channel pairs per packed FMA (bit-identical to the scalar loop)
+        add2(bsum[r], bsum[r + 1], gv[r], gv[r + 1]);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-          for (int k = 0; k < K; ++k) acc[r][q][k] = fmaf(gv[r], av[q][k], acc[r][q][k]);
+          for (int k = 0; k < K; ++k) fma2_acc(acc[r][q][k], acc[r + 1][q][k], gv[r], gv[r + 1], av[q][k], av[q][k]);
       }
     }
   }
