@@ -98,18 +98,28 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_f32_kernel(const ConvArgs
   const float* in_b = a.in + (long long)b * a.in_bs;
   for (int ci0 = 0; ci0 < a.C_in; ci0 += kCiTile) {
     __syncthreads();
-    // stage inputs with the prologue applied once per element
-    for (int idx = tid; idx < kCiTile * W_in; idx += kConvThreads) {
-      const int ci = idx / W_in, p = idx - ci * W_in;
-      const int u = t0 - halo + p;
+    // stage inputs with the prologue applied once per element: a warp per channel row, lanes along time (coalesced,
+    // no index division; the affine of the row is loaded once)
+    for (int ci = warp; ci < kCiTile; ci += kConvWarps) {
       const int c = ci0 + ci;
-      float v = 0.f;
-      if (c < a.C_in && u >= 0 && u < a.T_out) {
-        v = __ldg(in_b + (long long)c * a.in_cs + (u / a.up) * a.down);
-        if (a.pre_a) v = fmaf(v, __ldg(a.pre_a + b * a.C_in + c), __ldg(a.pre_c + b * a.C_in + c));
-        if (a.pre_lrelu) v = lrelu(v, a.slope);
+      const bool row_ok = c < a.C_in;
+      const float* row = in_b + (long long)(row_ok ? c : 0) * a.in_cs;
+      float pa = 1.f, pc = 0.f;
+      if (a.pre_a && row_ok) {
+        pa = __ldg(a.pre_a + b * a.C_in + c);
+        pc = __ldg(a.pre_c + b * a.C_in + c);
       }
-      in_s[idx] = v;
+      float* dst = in_s + ci * W_in;
+      for (int p = lane; p < W_in; p += 32) {
+        const int u = t0 - halo + p;
+        float v = 0.f;
+        if (row_ok && u >= 0 && u < a.T_out) {
+          v = __ldg(row + (a.up == 1 ? u : u / a.up) * a.down);
+          if (a.pre_a) v = fmaf(v, pa, pc);
+          if (a.pre_lrelu) v = lrelu(v, a.slope);
+        }
+        dst[p] = v;
+      }
     }
     for (int idx = tid; idx < kCiTile * K * CO_T; idx += kConvThreads) {
       const int ci = idx / (K * CO_T), rem = idx - ci * (K * CO_T);

@@ -78,21 +78,36 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_kernel(const WgradArgs 
   for (int ch = c_begin; ch < c_end; ++ch) {
     const int b = ch / n_tt, t0 = (ch - b * n_tt) * kWgTT;
     __syncthreads();
-    for (int idx = tid; idx < kWgCo * kWgTT; idx += kWgThreads) {
-      const int co = idx / kWgTT, p = idx - co * kWgTT;
-      const int c = co0 + co, t = t0 + p;
-      g_s[idx] = (c < a.C_out && t < a.T) ? __ldg(a.g + (long long)b * a.g_bs + (long long)c * a.g_cs + t) : 0.f;
-    }
-    for (int idx = tid; idx < kWgCi * W; idx += kWgThreads) {
-      const int ci = idx / W, p = idx - ci * W;
-      const int c = ci0 + ci, u = t0 - halo + p;
-      float v = 0.f;
-      if (c < a.C_in && u >= 0 && u < a.T) {
-        v = __ldg(a.x + (long long)b * a.x_bs + (long long)c * a.x_cs + (u / a.up) * a.down);
-        if (a.pre_a) v = fmaf(v, __ldg(a.pre_a + b * a.C_in + c), __ldg(a.pre_c + b * a.C_in + c));
-        if (a.pre_lrelu) v = lrelu(v, a.slope);
+    // staging: a warp per channel row, lanes along time (coalesced, no index division, the row's affine loaded once)
+    for (int co = warp; co < kWgCo; co += kWgThreads / 32) {
+      const int c = co0 + co;
+      const float* row = a.g + (long long)b * a.g_bs + (long long)(c < a.C_out ? c : 0) * a.g_cs + t0;
+      const int n_ok = c < a.C_out ? min(kWgTT, a.T - t0) : 0;
+#pragma unroll
+      for (int i = 0; i < kWgTT / 32; ++i) {
+        const int p = lane + 32 * i;
+        g_s[co * kWgTT + p] = p < n_ok ? __ldg(row + p) : 0.f;
       }
-      a_s[idx] = v;
+    }
+    for (int ci = warp; ci < kWgCi; ci += kWgThreads / 32) {
+      const int c = ci0 + ci;
+      const bool row_ok = c < a.C_in;
+      const float* row = a.x + (long long)b * a.x_bs + (long long)(row_ok ? c : 0) * a.x_cs;
+      float pa = 1.f, pc = 0.f;
+      if (a.pre_a && row_ok) {
+        pa = __ldg(a.pre_a + b * a.C_in + c);
+        pc = __ldg(a.pre_c + b * a.C_in + c);
+      }
+      for (int p = lane; p < W; p += 32) {
+        const int u = t0 - halo + p;
+        float v = 0.f;
+        if (row_ok && u >= 0 && u < a.T) {
+          v = __ldg(row + (a.up == 1 ? u : u / a.up) * a.down);
+          if (a.pre_a) v = fmaf(v, pa, pc);
+          if (a.pre_lrelu) v = lrelu(v, a.slope);
+        }
+        a_s[ci * W + p] = v;
+      }
     }
     __syncthreads();
 #pragma unroll 2
