@@ -168,6 +168,14 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_f32_kernel(const ConvArgs
     const int co = co0 + warp * RC + i;
     if (co >= a.C_out) break;  // warp-uniform
     const float bias = a.bias ? __ldg(a.bias + co) : 0.f;
+    // row pointers and per-(b, co) constants once per output channel: the step loop only adds t
+    const float* mask_row = a.mask ? a.mask + (long long)b * a.mask_bs + (long long)co * a.mask_cs : nullptr;
+    const float ma = (a.mask && a.mask_a) ? __ldg(a.mask_a + b * a.C_out + co) : 1.f;
+    const float mc = (a.mask && a.mask_a) ? __ldg(a.mask_c + b * a.C_out + co) : 0.f;
+    const float* res_row = a.res ? a.res + (long long)b * a.res_bs + (long long)co * a.res_cs : nullptr;
+    float* raw_row = a.raw ? a.raw + (long long)b * a.raw_bs + (long long)co * a.raw_cs : nullptr;
+    const long long gb_off = (long long)b * a.gb_bs + (long long)co * a.gb_cs;
+    float* out_row = a.out ? a.out + (long long)b * a.out_bs + (long long)co * a.out_cs : nullptr;
     float vals[RT];
     float s1 = 0.f;
 #pragma unroll
@@ -175,19 +183,16 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_f32_kernel(const ConvArgs
       const int t = t0 + lane + 32 * j;
       float v = acc[i][j] + bias;
       if (t < a.T_out) {
-        if (a.mask) {
-          float m = __ldg(a.mask + (long long)b * a.mask_bs + (long long)co * a.mask_cs + (t / a.mask_up) * a.mask_down);
-          if (a.mask_a) m = fmaf(m, __ldg(a.mask_a + b * a.C_out + co), __ldg(a.mask_c + b * a.C_out + co));
+        if (mask_row) {
+          float m = __ldg(mask_row + (a.mask_up == 1 ? t : t / a.mask_up) * a.mask_down);
+          if (a.mask_a) m = fmaf(m, ma, mc);
           v *= m > 0.f ? 1.f : a.slope;   // torch leaky_relu backward: x > 0 ? g : g * slope
         }
-        if (a.res) v += __ldg(a.res + (long long)b * a.res_bs + (long long)co * a.res_cs + t);
-        if (a.raw) a.raw[(long long)b * a.raw_bs + (long long)co * a.raw_cs + t] = v;
+        if (res_row) v += __ldg(res_row + t);
+        if (raw_row) raw_row[t] = v;
         if (a.post_lrelu) v = lrelu(v, a.slope);
-        if (a.gamma) {
-          const long long gi = (long long)b * a.gb_bs + (long long)co * a.gb_cs + t;
-          v = fmaf(__ldg(a.gamma + gi), v, __ldg(a.beta + gi));
-        }
-        if (a.out) a.out[(long long)b * a.out_bs + (long long)co * a.out_cs + t] = v;
+        if (a.gamma) v = fmaf(__ldg(a.gamma + gb_off + t), v, __ldg(a.beta + gb_off + t));
+        if (out_row) out_row[t] = v;
         s1 += v;
       } else {
         v = 0.f;
