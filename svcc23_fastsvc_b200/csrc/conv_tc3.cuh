@@ -23,25 +23,20 @@
 
 namespace fsvc {
 
-// Two CTA shapes of the same kernel:
-//   BIG   (512 threads, one CTA per SM): weights warp, MMA warp, 6 transform warps, 8 epilogue warps -- any conv;
-//   SMALL (224 threads, two CTAs per SM): weights+MMA warp, 2 transform warps, 4 epilogue warps -- convs whose
-//         weights are resident and whose rings fit in half the shared memory (C <= 48): two independent pipelines
-//         per SM double the loads in flight, which is what bounds the long low-channel layers (HBM latency).
-template <bool SMALL>
+// Role split of the 512-thread CTA (one CTA per SM): weights + row-loader warp, MMA warp, 6 transform warps, 8 epilogue
+// warps.  (Measured and dropped: two 224-thread CTAs per SM -- no faster on any layer; 10 transform + 4 epilogue warps
+// for the plain-epilogue layers -- slower on every conv with a residual.)
 struct Tc3Shape {
-  static constexpr int kMmaWarp = SMALL ? 0 : 1;
-  static constexpr int kX0 = SMALL ? 1 : 2;            // first transform warp
-  static constexpr int kXW = SMALL ? 2 : 6;            // transform warps
+  static constexpr int kMmaWarp = 1;
+  static constexpr int kX0 = 2;                         // first transform warp
+  static constexpr int kXW = 6;                         // transform warps
   static constexpr int kE0 = kX0 + kXW;                // first epilogue warp
-  static constexpr int kEW = SMALL ? 4 : 8;            // epilogue warps (4 lane quarters x kEH column halves)
+  static constexpr int kEW = 8;                         // epilogue warps (4 lane quarters x kEH column halves)
   static constexpr int kEH = kEW / 4;
   static constexpr int kXT = 32 * kXW, kET = 32 * kEW;
   static constexpr int kThreads = 32 * (kE0 + kEW);
-  static constexpr int kMinCtas = SMALL ? 2 : 1;
 };
-constexpr int kTc3Threads = Tc3Shape<false>::kThreads;
-constexpr int kTc3ThreadsSmall = Tc3Shape<true>::kThreads;
+constexpr int kTc3Threads = Tc3Shape::kThreads;
 constexpr int kTc3ChunkItems = 4;      // 16-byte-chunk items per transform thread and prefetch chunk
 
 struct Tc3Cfg {
@@ -215,30 +210,29 @@ enum {  // mbarrier indices
 // Shared-memory plan of one launch.  Returns false when even a 1-deep A ring does not fit.
 // cpw_force = 4 / 6: lean transform (MODE 3 / 4 / 5).  bulk = true (MODE 3 / 4): a staging slot holds the 6 aligned
 // 32-row blocks of the input that cover an item's window, filled by cp.async.bulk.
-__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool small = false, int cpw_force = 0,
-                                   bool bulk = false, bool direct = false) {
+__host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, int cpw_force = 0, bool bulk = false,
+                                   bool direct = false) {
   const int halo = (K / 2) * a.dil, W = kTc2M + 2 * halo;
   const uint32_t Gb = a.CIB / 8;
   c->a_bytes = 2u * Gb * W * 16u;
   c->b_bytes = 2u * K * Gb * a.N_tile * 16u;
   const int nvalid_max = a.C_out < a.N_tile ? a.C_out : a.N_tile;
   // epilogue sub-tile: a thread owns nsub / (column halves) channels, at most 16
-  const int eh = small ? 1 : 2;
+  const int eh = Tc3Shape::kEH;
   int nsub = 8 * eh;
   for (int cand : {12 * eh, 16 * eh, 8 * eh, 4 * eh})
     if (nvalid_max % cand == 0) {
       nsub = cand;
       break;
     }
-  if (small && (!a.w_resident || nvalid_max % nsub != 0)) return false;
   c->nsub = nsub;
   c->scr_pitch = nsub / eh <= 12 ? 12 : 20;
   const uint32_t w_bytes = a.w_resident ? c->b_bytes * a.n_blk : 0u;
-  const uint32_t scr_bytes = (small ? 4u : 8u) * (32u * c->scr_pitch + 16u) * 4u;
-  const uint32_t budget = small ? 113u * 1024u : 227u * 1024u;
+  const uint32_t scr_bytes = (uint32_t)Tc3Shape::kEW * (32u * c->scr_pitch + 16u) * 4u;
+  const uint32_t budget = 227u * 1024u;
   const uint32_t pa_bytes = 3u * 2u * ((a.C_in + 7) / 8 * 8) * 4u;  // triple-buffered per-utterance affine
   // Preference: deep staging (loads in flight) first, then A ring depth.
-  const uint32_t xw = small ? 2u : 6u;
+  const uint32_t xw = (uint32_t)Tc3Shape::kXW;
   // {A ring slots, staging depth, tasks per warp and chunk}: deep staging first, then A ring depth; half-size chunks
   // (half the staging memory) before giving up the double-buffered A ring
   static const int pref[][3] = {{3, 3, 4}, {2, 3, 4}, {3, 2, 4}, {2, 2, 4}, {3, 1, 4}, {2, 1, 4},
@@ -270,7 +264,7 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
     c->off_bias = off;
     off += (uint32_t)((a.N_tile + 3) / 4) * 16u;  // this N tile's bias, staged once by the epilogue warps
     c->off_fin = off;
-    off += a.pre_stats ? (uint32_t)(small ? 64 : 192) * 32u : 0u;  // statistics merge scratch: 4 doubles per thread
+    off += a.pre_stats ? (uint32_t)Tc3Shape::kXT * 32u : 0u;  // statistics merge scratch: 4 doubles per thread
     c->off_tab = off;
     off += Gb * (uint32_t)((W + 31) / 32) * 16u;  // transform geometry table
     c->off_stg = off;
@@ -288,10 +282,10 @@ __host__ inline bool tc3_plan_smem(const Tc2Args& a, int K, Tc3Cfg* c, bool smal
 // GEN: the A operand is generated from a 1-channel signal (first conv of an unfused level-0 chain).
 // MODE: 0 = table-driven transform (source row = window row * down), 1 = GEN, 2 = nearest-repeat input (up > 1,
 // down == 1): every source row is converted once and stored to its `up` window rows.
-template <int K, int NH4, bool SMALL, int MODE>
-__global__ void __launch_bounds__(Tc3Shape<SMALL>::kThreads, Tc3Shape<SMALL>::kMinCtas)
+template <int K, int NH4, int MODE>
+__global__ void __launch_bounds__(Tc3Shape::kThreads, 1)
 conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
-  using SH = Tc3Shape<SMALL>;
+  using SH = Tc3Shape;
   constexpr int kTc3XformThreads = SH::kXT, kTc3EpiThreads = SH::kET;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* const smem = smem_raw;

@@ -70,18 +70,18 @@ static bool tc2_plan(int C_in, int C_out, int K, ConvW* cw) {
 
 int tc_setup_kernels() {
   const int max_smem = 227 * 1024;
-#define FSVC_ATTR(K_, NH_, SM_)                                                                                         \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, SM_, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
-  FSVC_ATTR(3, 3, false);
-  FSVC_ATTR(3, 0, false);
-  FSVC_ATTR(1, 3, false);
-  FSVC_ATTR(1, 0, false);
+#define FSVC_ATTR(K_, NH_)                                                                                        \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+  FSVC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<K_, NH_, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem))
+  FSVC_ATTR(3, 3);
+  FSVC_ATTR(3, 0);
+  FSVC_ATTR(1, 3);
+  FSVC_ATTR(1, 0);
 #undef FSVC_ATTR
   FSVC_CUDA(cudaFuncSetAttribute(level0_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   return FSVC_OK;
@@ -256,22 +256,18 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   cfg.m_tiles = (p[0].T_out + kTc2M - 1) / kTc2M;
   const int groups = n_prob * p[0].n_ntiles;
   const int items = (b_hi - b_lo) * cfg.m_tiles;
-  // two half-size CTAs per SM when the conv allows it and there is enough work to keep both pipelines busy
-  // (measured: two 224-thread CTAs per SM are no faster than one 512-thread CTA on any layer -- kept as a template
-  //  option of the kernel, not instantiated)
-  const bool small = false;
   // transform variant: 3 / 4 = lean path (direct rows, one ci block, a warp's <= 4 / <= 6 tasks of an item in one chunk)
   int mode = p[0].gen_w ? 1 : (p[0].up > 1 ? 2 : 0);
   if (mode == 0 && p[0].down == 1 && !p[0].in_pl && !getenv("FSVC_NO_LEAN")) {
     const int ntask = (p[0].CIB / 8) * ((kTc2M + 2 * (K / 2) * p[0].dil + 31) / 32);
     const int rounds = (ntask + 5) / 6;
     const bool bulk = (K / 2) * p[0].dil <= 32;  // the window spans at most 6 aligned 32-row blocks
-    if (bulk && rounds <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4, true)) mode = 3;
-    else if (bulk && rounds <= 6 && tc3_plan_smem(p[0], K, &cfg, false, 6, true) && cfg.a_slots >= 2) mode = 4;
+    if (bulk && rounds <= 4 && tc3_plan_smem(p[0], K, &cfg, 4, true)) mode = 3;
+    else if (bulk && rounds <= 6 && tc3_plan_smem(p[0], K, &cfg, 6, true) && cfg.a_slots >= 2) mode = 4;
   }
   if (p[0].in_pl) {  // operand planes written by the producer: no transform role
     if (mode != 0 || p[0].down != 1 || (K / 2) * p[0].dil > kPlPad || p[0].C_in % 8 != 0 || p[0].C_in % p[0].CIB != 0 ||
-        !tc3_plan_smem(p[0], K, &cfg, false, 0, false, true)) {
+        !tc3_plan_smem(p[0], K, &cfg, 0, false, true)) {
       c.err = 3;
       return;
     }
@@ -280,13 +276,13 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
   if (mode == 2 && p[0].down == 1 && p[0].up <= 8 && p[0].n_blk == 1 && !getenv("FSVC_NO_LEAN")) {
     const int Wd = kTc2M + 2 * (K / 2) * p[0].dil;
     const int ntask = (p[0].CIB / 8) * (((Wd + p[0].up - 1) / p[0].up + 1 + 31) / 32);
-    if ((ntask + 5) / 6 <= 4 && tc3_plan_smem(p[0], K, &cfg, false, 4)) mode = 5;
+    if ((ntask + 5) / 6 <= 4 && tc3_plan_smem(p[0], K, &cfg, 4)) mode = 5;
   }
-  if (mode < 3 && !tc3_plan_smem(p[0], K, &cfg, false)) {
+  if (mode < 3 && !tc3_plan_smem(p[0], K, &cfg)) {
     c.err = 1;
     return;
   }
-  int per_group = (small ? 2 : 1) * h->num_sms / groups;
+  int per_group = h->num_sms / groups;
   per_group = per_group < 1 ? 1 : per_group;
   per_group = per_group > items ? items : per_group;
   const dim3 grid(per_group * groups);
@@ -305,24 +301,24 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
             c.label, name, p[0].C_in, p[0].C_out, K, p[0].dil, p[0].up, p[0].down, p[0].CIB, p[0].n_blk, p[0].N_tile,
             p[0].n_ntiles, p[0].w_resident, cfg.a_slots, cfg.stg_depth, cfg.total, grid.x, items);
   // compile-time epilogue width (12 channels per thread) when every sub-tile of every N tile is full
-  const int per_thread = cfg.nsub / (small ? 1 : 2);
+  const int per_thread = cfg.nsub / Tc3Shape::kEH;
   const bool nh3 = per_thread == 12 && p[0].C_out % cfg.nsub == 0 && (p[0].n_ntiles == 1 || p[0].N_tile % cfg.nsub == 0) &&
                    !p[0].gres_w;  // the generated residual lives in the run-time-width instantiation only
-  const int threads = small ? kTc3ThreadsSmall : kTc3Threads;
-#define FSVC_TC3(K_, NH_, SM_)                                                                               \
+  const int threads = kTc3Threads;
+#define FSVC_TC3(K_, NH_)                                                                              \
   do {                                                                                                      \
-    if (mode == 1) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 1>, grid, threads, cfg.total, c.stream, L);      \
-    else if (mode == 2) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 2>, grid, threads, cfg.total, c.stream, L); \
-    else if (mode == 3) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 3>, grid, threads, cfg.total, c.stream, L); \
-    else if (mode == 4) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 4>, grid, threads, cfg.total, c.stream, L); \
-    else if (mode == 5) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 5>, grid, threads, cfg.total, c.stream, L); \
-    else if (mode == 6) launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 6>, grid, threads, cfg.total, c.stream, L); \
-    else launch_pdl(conv_tc3_kernel<K_, NH_, SM_, 0>, grid, threads, cfg.total, c.stream, L);                \
+    if (mode == 1) launch_pdl(conv_tc3_kernel<K_, NH_, 1>, grid, threads, cfg.total, c.stream, L);      \
+    else if (mode == 2) launch_pdl(conv_tc3_kernel<K_, NH_, 2>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 3) launch_pdl(conv_tc3_kernel<K_, NH_, 3>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 4) launch_pdl(conv_tc3_kernel<K_, NH_, 4>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 5) launch_pdl(conv_tc3_kernel<K_, NH_, 5>, grid, threads, cfg.total, c.stream, L); \
+    else if (mode == 6) launch_pdl(conv_tc3_kernel<K_, NH_, 6>, grid, threads, cfg.total, c.stream, L); \
+    else launch_pdl(conv_tc3_kernel<K_, NH_, 0>, grid, threads, cfg.total, c.stream, L);                \
   } while (0)
   if (K == 3) {
-    if (nh3) FSVC_TC3(3, 3, false); else FSVC_TC3(3, 0, false);
+    if (nh3) FSVC_TC3(3, 3); else FSVC_TC3(3, 0);
   } else {
-    if (nh3) FSVC_TC3(1, 3, false); else FSVC_TC3(1, 0, false);
+    if (nh3) FSVC_TC3(1, 3); else FSVC_TC3(1, 0);
   }
 #undef FSVC_TC3
   double flops = 0, elems = 0;
