@@ -60,6 +60,7 @@ struct Tc3Launch {
   int hetero;  // epilogue flags and tensors), instead of pointer deltas against problem 0
   long long d_in, d_w, d_bias, d_gen_w, d_gen_b, d_res, d_gres_w, d_gres_b, d_gres_x, d_raw, d_out;  // elements
   long long d_in_pl, d_out_pl;  // 16-byte chunks
+  long long d_out_dec;          // elements
   Tc3Cfg c;
   int tl_slot;  // launch index inside the forward (event timeline builds only)
 };
@@ -1350,6 +1351,8 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
       const float* gres_x = gres_w ? a.gres_x + prob * L.d_gres_x : nullptr;
       float* raw = (!PLAIN && a.raw) ? a.raw + prob * L.d_raw : nullptr;
       uint4* out_pl = (PLAIN && a.out_pl) ? a.out_pl + prob * L.d_out_pl : nullptr;  // operand planes (ntc_common.cuh)
+      float* out_dec = (PLAIN && a.out_dec) ? a.out_dec + prob * L.d_out_dec : nullptr;
+      const long long Tp_dec = out_dec ? ntc_tp(a.out_dec_T) : 0;
       float* out = a.out ? a.out + prob * L.d_out : nullptr;
       const bool has_film = !PLAIN && a.gamma != nullptr, has_res = res != nullptr, has_stats = !PLAIN && a.stats != nullptr;
       const bool has_last = !PLAIN && a.last_w != nullptr;
@@ -1427,6 +1430,12 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
         const unsigned long long rb = row_block(b, tile);
         float* raw_row = raw ? raw + rb * (uint32_t)a.raw_ld + lane * 4 : nullptr;
         float* out_row = out ? out + rb * (uint32_t)a.out_ld + lane * 4 : nullptr;
+        // decimated copy: this thread's step is kept when it is a multiple of r
+        float* dec_row = nullptr;
+        if (out_dec && ok) {
+          const int td = t / a.out_dec_r;
+          if (td * a.out_dec_r == t) dec_row = out_dec + ntc_row(Tp_dec, a.out_dec_ld, b, td);
+        }
         // this thread's row in group 0 of the operand planes; pad_rows: 0, or -/+ kPlPad when the thread also owns a
         // zero row in front of the utterance (first tile, first 8 steps) / behind its last tile
         uint4* pl_row = out_pl ? out_pl + (long long)b * a.out_pl_G * a.out_pl_Tp + (kPlPad + t) : nullptr;
@@ -1486,6 +1495,7 @@ conv_tc3_kernel(const __grid_constant__ Tc3Launch L) {
                 }
               }
               if (out_row && ok) reinterpret_cast<float4*>(out_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
+              if (PLAIN && dec_row) reinterpret_cast<float4*>(dec_row + (co >> 2) * 128)[32 * j] = make_float4(x[0], x[1], x[2], x[3]);
               if (PLAIN && pl_row) {
                 // 4 channels = half of a (step, group) chunk in each plane; steps past the utterance's end are zeros
                 float y[4] = {x[0], x[1], x[2], x[3]};

@@ -72,6 +72,10 @@ struct Tc2Args {
   long long out_pl_lo;
   int out_pl_G, out_pl_Tp;
   int out_pl_lrelu;      // LeakyReLU before the split (the consumer's prologue, applied once here)
+  // ---- decimated copy (plain epilogue): steps t with t % out_dec_r == 0 also go to out_dec[b][t / out_dec_r], the
+  // next level's input at its own rate -- its first convs then read contiguous rows instead of every r-th one
+  float* out_dec;        // NTC [B][out_dec_T][out_dec_ld], or nullptr
+  int out_dec_ld, out_dec_T, out_dec_r;
 };
 constexpr int kPlPad = 8;
 

@@ -102,6 +102,7 @@ struct WS2 {
   float *pa, *pc;                // [B][C]
   float* xin;                    // [B][frames][in_channels] channels-last copy of the PPG input
   float* ydec[2];                // [B][T/s][C0] level-0 output decimated for level 1 (fused level kernel)
+  float* ydec_l[2][FSVC_MAX_STAGES];  // [B][T_l/s][C_l] output of level l >= 1 decimated for level l + 1 (d4's epilogue)
 };
 
 // rows per (utterance, 8-channel group) of an operand-plane tensor: whole 128-step tiles + kPlPad zero rows at both ends
@@ -122,6 +123,8 @@ static size_t layout_ws2(const fsvc_handle* h, int B, int frames, void* base, si
     max_lvl = ne > max_lvl ? ne : max_lvl;
     max_lvl = ne_pl > max_lvl ? ne_pl : max_lvl;
     for (int br = 0; br < 2; ++br) ws->y[br][l] = ar.get<float>(ne);
+    for (int br = 0; br < 2; ++br)
+      ws->ydec_l[br][l] = (l >= 1 && l + 1 < n) ? ar.get<float>((size_t)B * h->lvl_c[l] * ntc_tp(T_l / h->dscale[l + 1])) : nullptr;
     ws->H[l] = ar.get<float>(2 * (ne_pl > ne ? ne_pl : ne));
     ws->GB[l] = ar.get<float>(2 * ne);
   }
@@ -216,7 +219,8 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     if (x.up != y.up || x.down != y.down || x.dil != y.dil || x.C_in != y.C_in || x.C_out != y.C_out ||
         x.T_out != y.T_out || x.T_in != y.T_in || x.in_ld != y.in_ld || x.CIB != y.CIB || x.n_blk != y.n_blk ||
         x.N_tile != y.N_tile || x.n_ntiles != y.n_ntiles || x.w_resident != y.w_resident || x.gen_w || y.gen_w ||
-        x.pre_stats || y.pre_stats || x.pre_a || y.pre_a || x.in_pl || y.in_pl || x.out_pl || y.out_pl) {
+        x.pre_stats || y.pre_stats || x.pre_a || y.pre_a || x.in_pl || y.in_pl || x.out_pl || y.out_pl || x.out_dec ||
+        y.out_dec) {
       c.err = 2;
       return;
     }
@@ -235,6 +239,7 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     L.d_out = x.out ? y.out - x.out : 0;
     L.d_in_pl = x.in_pl ? y.in_pl - x.in_pl : 0;
     L.d_out_pl = x.out_pl ? y.out_pl - x.out_pl : 0;
+    L.d_out_dec = x.out_dec ? y.out_dec - x.out_dec : 0;
     // everything that is not a per-problem pointer must agree
     if ((x.up > 1 && x.down > 1) || x.pre_lrelu != y.pre_lrelu || x.post_lrelu != y.post_lrelu || x.gamma != y.gamma || x.stats != y.stats ||
         x.pre_a != y.pre_a || x.up != y.up || x.down != y.down || x.dil != y.dil || x.C_in != y.C_in ||
@@ -242,7 +247,8 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
         x.out_ld != y.out_ld || x.res_ld != y.res_ld || (x.res == nullptr) != (y.res == nullptr) ||
         (x.gen_w == nullptr) != (y.gen_w == nullptr) || (x.gres_w == nullptr) != (y.gres_w == nullptr) ||
         (x.in_pl == nullptr) != (y.in_pl == nullptr) || (x.out_pl == nullptr) != (y.out_pl == nullptr) ||
-        x.in_pl_lo != y.in_pl_lo || x.out_pl_lo != y.out_pl_lo || x.out_pl_lrelu != y.out_pl_lrelu) {
+        x.in_pl_lo != y.in_pl_lo || x.out_pl_lo != y.out_pl_lo || x.out_pl_lrelu != y.out_pl_lrelu ||
+        (x.out_dec == nullptr) != (y.out_dec == nullptr) || x.out_dec_r != y.out_dec_r) {
       c.err = 2;
       return;
     }
@@ -328,6 +334,7 @@ static void launch_tc2(Ctx& c, const fsvc_handle* h, int K, const Tc2Args* p, in
     flops += 2.0 * a.C_in * a.C_out * K * BT;
     elems += a.gen_w ? BT : (double)(b_hi - b_lo) * a.C_in * ((double)a.T_out / a.up);
     elems += BT * a.C_out * ((a.out ? 1 : 0) + (a.out_pl ? 1 : 0) + (a.raw ? 1 : 0) + (a.res ? 1 : 0) + (a.gamma ? 2 : 0));
+    if (a.out_dec) elems += BT * a.C_out / a.out_dec_r;
     if (a.last_w) {  // folded conv_last
       flops += 2.0 * BT * a.C_out * a.last_co;
       elems += BT * a.last_co + (double)a.C_out * a.last_co;
@@ -396,7 +403,7 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
   if (!h->l0_fused && h->sig_ready[1]) cudaStreamWaitEvent(stream, h->sig_ready[1], 0);
   // ---- conditioning chains, both branches per launch (fastsvc.py:180-193, 220-232) ----
   int T_prev = T, T_l = T;
-  bool fused_l0 = false;
+  bool fused_l0 = false, dec_prev = false;
   for (int l = 0; l < n; ++l) {
     T_l = T_prev / h->dscale[l];
     const LevelW& lw = h->level[l];
@@ -405,6 +412,8 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
     Tc2Args p[2];
     bool use_pl = false;
     const int pl_Tp = pl_rows(T_l);
+    // this level's last conv also writes its output decimated for the next level
+    const bool dec_out = l >= 1 && l + 1 < n && h->dscale[l + 1] > 1 && T_l % h->dscale[l + 1] == 0 && !getenv("FSVC_NO_DEC");
     // operand planes of this level: `buf` holds the hi plane [B][G][pl_Tp] chunks, then the lo plane
     auto planes_out = [&](Tc2Args& a, float* buf, int G, int g0, int lrelu) {
       a.out_pl = reinterpret_cast<uint4*>(buf) + (long long)g0 * pl_Tp;
@@ -494,10 +503,11 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
       launch_tc2(c, h, 3, p, 2, "down_d4+r");
     } else {
       const int Cp = h->lvl_c[l - 1];
-      // the fused level-0 kernel hands over its output already decimated
-      const bool dec_in = l == 1 && fused_l0;
+      // the fused level-0 kernel / the previous level's last conv hand over their output already decimated
+      const bool dec_in = (l == 1 && fused_l0) || (l >= 2 && dec_prev);
+      const float* const ydec_in[2] = {l == 1 ? ws.ydec[0] : ws.ydec_l[0][l - 1], l == 1 ? ws.ydec[1] : ws.ydec_l[1][l - 1]};
       for (int br = 0; br < 2; ++br) {
-        p[br] = tc2_args(c, lw.r1[br], dec_in ? ws.ydec[br] : ws.y[br][l - 1], Cp, dec_in ? T_l : T_prev, T_l, 1,
+        p[br] = tc2_args(c, lw.r1[br], dec_in ? ydec_in[br] : ws.y[br][l - 1], Cp, dec_in ? T_l : T_prev, T_l, 1,
                          ws.tr[br], C);
         p[br].down = dec_in ? 1 : h->dscale[l];
       }
@@ -511,7 +521,7 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
       use_pl = C % 8 == 0 && C % lw.c2[0].tc2.CIB == 0 && C % lw.c4[0].tc2.CIB == 0 && (2 * C) % lw.film_out.tc2.CIB == 0 &&
                lvl_items <= 6ll * h->num_sms && !getenv("FSVC_NO_PLANES");
       for (int br = 0; br < 2; ++br) {
-        p[br] = tc2_args(c, lw.c1[br], dec_in ? ws.ydec[br] : ws.y[br][l - 1], Cp, dec_in ? T_l : T_prev, T_l, 1,
+        p[br] = tc2_args(c, lw.c1[br], dec_in ? ydec_in[br] : ws.y[br][l - 1], Cp, dec_in ? T_l : T_prev, T_l, 1,
                          use_pl ? nullptr : ws.ta[br], C);
         p[br].down = dec_in ? 1 : h->dscale[l];
         p[br].pre_lrelu = 1;
@@ -533,8 +543,15 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
         p[br].res = ws.tr[br];
         p[br].res_ld = C;
         if (use_pl) planes_in(p[br], ws.tb[br], C / 8);
+        if (dec_out) {
+          p[br].out_dec = ws.ydec_l[br][l];
+          p[br].out_dec_ld = C;
+          p[br].out_dec_T = T_l / h->dscale[l + 1];
+          p[br].out_dec_r = h->dscale[l + 1];
+        }
       }
       launch_tc2(c, h, 3, p, 2, "down_d4");
+      dec_prev = dec_out;
     }
     for (int br = 0; br < 2; ++br) {
       p[br] = tc2_args(c, lw.film[br], ws.y[br][l], C, T_l, T_l, 1, use_pl ? nullptr : ws.H[l] + ntc_col(br * C), 2 * C);
