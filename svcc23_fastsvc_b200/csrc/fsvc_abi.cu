@@ -440,6 +440,8 @@ int fsvc_create(const fsvc_config* cfg, fsvc_handle** out) {
       cudaEventCreateWithFlags(&h->ev_out_done, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_sig[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_sig[1], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_sig[2], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_sig[3], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_ppg, cudaEventDisableTiming) != cudaSuccess) {
     fsvc_destroy(h);
     return fail(FSVC_E_CUDA, "cannot create the upload stream / events");
@@ -457,7 +459,7 @@ void fsvc_destroy(fsvc_handle* h) {
   if (h->jobs_tc) cudaFree(h->jobs_tc);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_ppg) cudaEventDestroy(h->ev_ppg);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < fsvc_handle::kSigParts; ++i)
     if (h->ev_sig[i]) cudaEventDestroy(h->ev_sig[i]);
   if (h->ev_out_half) cudaEventDestroy(h->ev_out_half);
   if (h->ev_out_done) cudaEventDestroy(h->ev_out_done);
@@ -676,34 +678,37 @@ int fsvc_forward_host(fsvc_handle* h, const float* ppg_host, const float* sine_h
   float* d_out = ar.get<float>(n_out);
   // All uploads go, in the order the forward needs them, on the copy stream (which starts after everything already
   // queued on the caller's stream, so the staging buffers of a previous call are never overwritten early): the two
-  // signals of the first half of the batch, those of the second half, the speaker vectors, the PPG tensor.  The forward
-  // waits for each piece where it first reads it: the full-rate conditioning level runs per half (the first half
-  // computes while the second is on the wire), the speaker projections and stage 0 wait for the rest.
-  const int B0 = (B + 1) / 2;  // measured at config 2: 1.400 ms without either overlap, 1.359 with this one, 1.350 with both
-  const size_t n0 = (size_t)B0 * T, n1 = n_sig - n0;
+  // signals in four batch parts, the speaker vectors, the PPG tensor.  The forward waits for each piece where it first
+  // reads it: the full-rate conditioning level runs per part (a part computes while the next ones are on the wire), the
+  // speaker projections and stage 0 wait for the rest.
+  // (measured at config 2: 1.400 ms without either overlap, 1.359 with two signal halves, 1.350 with the early waveform
+  //  half as well; on the final build 2 / 3 / 4 parts: 1.1505 / 1.147 / 1.141 ms -- the first kernel starts after 1 MB
+  //  instead of 2 MB of upload)
+  static const int want_parts = getenv("FSVC_SIG_PARTS") ? atoi(getenv("FSVC_SIG_PARTS")) : fsvc_handle::kSigParts;
+  int n_parts = want_parts < 1 ? 1 : (want_parts > fsvc_handle::kSigParts ? fsvc_handle::kSigParts : want_parts);
+  if (n_parts > B) n_parts = B;
   FSVC_CUDA(cudaEventRecord(h->ev_fork, s));
   FSVC_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_fork, 0));
-  FSVC_CUDA(cudaMemcpyAsync(d_sine, sine_host, n0 * 4, cudaMemcpyHostToDevice, h->copy_stream));
-  FSVC_CUDA(cudaMemcpyAsync(d_lft, lft_host, n0 * 4, cudaMemcpyHostToDevice, h->copy_stream));
-  FSVC_CUDA(cudaEventRecord(h->ev_sig[0], h->copy_stream));
-  if (n1) {
-    FSVC_CUDA(cudaMemcpyAsync(d_sine + n0, sine_host + n0, n1 * 4, cudaMemcpyHostToDevice, h->copy_stream));
-    FSVC_CUDA(cudaMemcpyAsync(d_lft + n0, lft_host + n0, n1 * 4, cudaMemcpyHostToDevice, h->copy_stream));
+  for (int k = 0; k <= n_parts; ++k) h->sig_bounds[k] = (int)((long long)k * B / n_parts);
+  for (int k = 0; k < n_parts; ++k) {
+    const size_t o = (size_t)h->sig_bounds[k] * T, n = (size_t)(h->sig_bounds[k + 1] - h->sig_bounds[k]) * T;
+    FSVC_CUDA(cudaMemcpyAsync(d_sine + o, sine_host + o, n * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    FSVC_CUDA(cudaMemcpyAsync(d_lft + o, lft_host + o, n * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    FSVC_CUDA(cudaEventRecord(h->ev_sig[k], h->copy_stream));
   }
-  FSVC_CUDA(cudaEventRecord(h->ev_sig[1], h->copy_stream));
   if (spk_host) FSVC_CUDA(cudaMemcpyAsync(d_spk, spk_host, n_spk * 4, cudaMemcpyHostToDevice, h->copy_stream));
   FSVC_CUDA(cudaMemcpyAsync(d_ppg, ppg_host, n_ppg * 4, cudaMemcpyHostToDevice, h->copy_stream));
   FSVC_CUDA(cudaEventRecord(h->ev_ppg, h->copy_stream));
   h->ppg_ready = h->ev_ppg;
-  h->sig_ready[0] = h->ev_sig[0];
-  h->sig_ready[1] = h->ev_sig[1];
-  h->sig_split = B0;
+  for (int k = 0; k < n_parts; ++k) h->sig_ready[k] = h->ev_sig[k];
+  h->sig_parts = n_parts;
   h->out_host = out_host;
   h->out_host_done = 0;
   rc = fsvc_forward(h, d_ppg, d_sine, d_lft, spk_host ? d_spk : nullptr, d_out, B, frames, (char*)workspace + ar.off,
                     workspace_bytes - ar.off, mode, stream_);
-  h->ppg_ready = h->sig_ready[0] = h->sig_ready[1] = nullptr;
-  h->sig_split = 0;
+  h->ppg_ready = nullptr;
+  for (int k = 0; k < fsvc_handle::kSigParts; ++k) h->sig_ready[k] = nullptr;
+  h->sig_parts = 0;
   h->out_host = nullptr;
   const size_t done = h->out_host_done;  // floats the forward already sent back on the copy stream
   h->out_host_done = 0;

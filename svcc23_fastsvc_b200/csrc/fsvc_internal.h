@@ -112,11 +112,14 @@ struct fsvc_handle {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_ppg = nullptr;
   cudaEvent_t ppg_ready = nullptr;  // set for the duration of one fsvc_forward_host call
-  // fsvc_forward_host: the two signals are uploaded in two batch halves; the fused level-0 kernel is launched per half
-  // so the first half computes while the second is still on the wire.  sig_ready[k] / sig_split are set for the call.
-  cudaEvent_t ev_sig[2] = {nullptr, nullptr};
-  cudaEvent_t sig_ready[2] = {nullptr, nullptr};
-  int sig_split = 0;  // utterances in the first half
+  // fsvc_forward_host: the two signals are uploaded in up to kSigParts batch parts; the fused level-0 kernel is launched
+  // per part, so a part computes while the next ones are still on the wire.  sig_ready[k] / sig_bounds / sig_parts are
+  // set for the call (sig_parts == 0: no split; part k = utterances [sig_bounds[k], sig_bounds[k + 1])).
+  static constexpr int kSigParts = 4;
+  cudaEvent_t ev_sig[kSigParts] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t sig_ready[kSigParts] = {nullptr, nullptr, nullptr, nullptr};
+  int sig_bounds[kSigParts + 1] = {0, 0, 0, 0, 0};
+  int sig_parts = 0;
   // fsvc_forward_host: host destination of the waveform (set for the call); the tensor-core forward copies the first
   // half back itself, while the last conv of the second half runs, and reports how many floats it has taken care of
   float* out_host = nullptr;

@@ -400,7 +400,7 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
   if (!prof) cudaEventRecord(h->ev_side_join, side);
 
   // fsvc_forward_host: without the fused level-0 kernel (which takes the signals half by half) wait for both halves here
-  if (!h->l0_fused && h->sig_ready[1]) cudaStreamWaitEvent(stream, h->sig_ready[1], 0);
+  if (!h->l0_fused && h->sig_parts > 0) cudaStreamWaitEvent(stream, h->sig_ready[h->sig_parts - 1], 0);
   // ---- conditioning chains, both branches per launch (fastsvc.py:180-193, 220-232) ----
   int T_prev = T, T_l = T;
   bool fused_l0 = false, dec_prev = false;
@@ -460,13 +460,12 @@ int forward_tc2(fsvc_handle* h, const float* ppg, const float* sine, const float
       fa.N2 = lw.film_out.nc_N;
       fa.slope = c.slope;
       if (level_fused_fill_desc(&fa) != 0) return fail(FSVC_E_INVALID, "internal: fused level descriptor table overflow");
-      // fsvc_forward_host uploads the signals in two batch halves: one launch per half, each behind its own event
-      const int n_part = (h->sig_ready[0] && h->sig_split > 0 && h->sig_split < B) ? 2 : 1;
+      // fsvc_forward_host uploads the signals in batch parts: one launch per part, each behind its own event
+      const int n_part = h->sig_parts > 0 ? h->sig_parts : 1;
       for (int part = 0; part < n_part; ++part) {
-        fa.b_off = part == 0 ? 0 : h->sig_split;
-        fa.B = n_part == 1 ? B : (part == 0 ? h->sig_split : B - h->sig_split);
-        if (h->sig_ready[part]) cudaStreamWaitEvent(stream, h->sig_ready[part], 0);
-        if (n_part == 1 && h->sig_ready[1]) cudaStreamWaitEvent(stream, h->sig_ready[1], 0);
+        fa.b_off = h->sig_parts > 0 ? h->sig_bounds[part] : 0;
+        fa.B = h->sig_parts > 0 ? h->sig_bounds[part + 1] - h->sig_bounds[part] : B;
+        if (h->sig_parts > 0) cudaStreamWaitEvent(stream, h->sig_ready[part], 0);
         const int items = fa.B * fa.n_tiles;
         const int grid = items < h->num_sms ? items : h->num_sms;
         launch_pdl(level0_fused_kernel, dim3(grid), kLfThreads, LF.total, stream, fa);
