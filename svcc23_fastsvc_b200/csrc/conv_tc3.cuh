@@ -4,20 +4,27 @@
 // as a four-role pipeline so that no role ever waits on HBM with nothing else to do:
 //
 //   warp 0      WEIGHTS    cp.async.bulk (UBLKCP) of the packed bf16 hi|lo weights: once when they fit in
-//                          shared memory, else one (N tile, ci block) chunk per MMA block through a 2-slot ring
+//               + ROWS     shared memory, else one (N tile, ci block) chunk per MMA block through a 2-slot ring.  The same
+//                          thread is the ROW LOADER of the direct layers (MODE 3 / 4: the <= 6 aligned 32-row blocks of
+//                          raw rows covering an item's window, bulk-copied into a staging ring; MODE 6: the producer's
+//                          bf16 hi|lo operand planes straight into the A ring)
 //   warp 1      MMA        one thread issues tcgen05.mma (bf16 3-term split, fp32 accumulation in TMEM,
 //                          two accumulators so tile i+1 is computed while tile i is drained)
-//   warps 2-7   TRANSFORM  128-bit loads of the A window, issued one 768-item chunk AHEAD of their use
-//                          (register double buffer) -> InstanceNorm affine -> LeakyReLU -> zero padding
-//                          -> bf16 hi|lo in the UMMA K-major canonical layout (taps = descriptor row shifts)
+//   warps 2-7   TRANSFORM  staged raw rows -> InstanceNorm affine -> LeakyReLU -> zero padding -> bf16 hi|lo in the
+//                          UMMA K-major canonical layout (taps = descriptor row shifts); packed fp32 arithmetic.
+//                          MODE 0 / 2 (decimated / wide nearest-repeat inputs) fetch their rows themselves with
+//                          per-lane cp.async one chunk ahead; MODE 1 generates the operand from a 1-channel signal;
+//                          MODE 6 has no transform work at all
 //   warps 8-15  EPILOGUE   TMEM -> registers (+bias, residual, FiLM affine) -> 128-bit row stores; the
 //                          residual / gamma / beta rows of the NEXT sub-tile are requested before the
 //                          current one is waited for; InstanceNorm partial statistics through a per-warp
-//                          shared-memory transpose
+//                          shared-memory transpose.  Two instantiations: plain (bias / residual / LeakyReLU / stores,
+//                          optionally operand planes and a decimated copy for the consumer) and general
 //
 // The roles meet only through mbarriers (full/empty pairs per ring slot, tcgen05.commit on the tensor-core
-// side).  One CTA per SM, a static round-robin list of (utterance, 128-step tile) items per CTA.
-// Activations are [B][T][C] fp32: every global access is a 128-bit access to a contiguous row segment.
+// side).  One CTA per SM, one contiguous range of (utterance, 128-step tile) items per CTA.
+// Activations are blocked channels-last fp32 ([B][T/32][C/4][32][4], ntc_common.cuh): every global access is a
+// 128-bit access or a bulk copy of a contiguous run.
 #pragma once
 #include "ntc_common.cuh"
 
